@@ -1,0 +1,115 @@
+"""CPU: pins the oracle against the reference's own golden vectors (tests/golden/, transcribed by
+oracle/make_golden.py from the reference test-suite) and against an independent float64 NumPy
+computation.  No GPU, no product code."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: c["name"])
+def test_reference_known_answers(case):
+    ds = np.array(case["dataset"], np.float32)
+    qs = np.array(case["queries"], np.float32)
+    keep = case.get("filter_keep")
+    if keep is not None:
+        sub = ds[keep]
+        dist, idx = oracle.knn(sub, qs, case["k"], case["metric"])
+        idx = np.array(keep)[idx]
+    else:
+        dist, idx = oracle.knn(ds, qs, case["k"], case["metric"])
+    assert idx.tolist() == case["neighbors"]
+    np.testing.assert_allclose(dist, np.array(case["distances"], np.float32), atol=case["eps"])
+
+
+def test_reference_label_case():
+    lc = GOLD["label_case"]
+    pts = np.array(lc["points"], np.float32)
+    labels = np.array(lc["labels"])
+    _, idx = oracle.knn(pts, pts, lc["k"], lc["metric"])
+    assert (labels[idx] == labels[:, None]).all()
+
+
+def test_fp8_known_answers():
+    for v, code in GOLD["fp8"]["unsigned"]:
+        assert int(oracle.fp8_encode([v])[0]) == code, v
+    for code, v in GOLD["fp8"]["decode_unsigned"]:
+        assert float(oracle.fp8_decode([code])[0]) == v
+    # signed variant: sign lives in the LSB (ivf_pq_fp_8bit.cuh:56-60, 76-80)
+    x = np.array([-1.0, 1.0, -3.5, 0.0], np.float32)
+    enc = oracle.fp8_encode(x, signed=True)
+    assert (enc & 1).tolist() == [1, 0, 1, 0]
+    dec = oracle.fp8_decode(enc, signed=True)
+    assert np.sign(dec[:3]).tolist() == [-1.0, 1.0, -1.0]
+    # monotone and within 2^-3 relative error (3 value bits, truncation + half-ulp bias)
+    v = np.exp(np.linspace(np.log(1e-4), np.log(6e4), 2000)).astype(np.float32)
+    r = oracle.fp8_decode(oracle.fp8_encode(v))
+    assert (np.diff(r) >= 0).all()
+    assert np.max(np.abs(r - v) / v) <= 0.125 / 2 + 1e-6
+
+
+@pytest.mark.parametrize("metric", ["sqeuclidean", "l2_unexpanded", "inner_product", "cosine", "euclidean"])
+def test_knn_against_float64(metric):
+    rng = np.random.default_rng(1234)
+    ds = rng.uniform(-1, 1, (500, 33)).astype(np.float32)
+    qs = rng.uniform(-1, 1, (40, 33)).astype(np.float32)
+    k = 7
+    dist, idx = oracle.knn(ds, qs, k, metric)
+    a, b = qs.astype(np.float64), ds.astype(np.float64)
+    if metric in ("sqeuclidean", "l2_unexpanded", "euclidean"):
+        full = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+        if metric == "euclidean":
+            full = np.sqrt(full)
+        order = np.argsort(full, axis=1, kind="stable")[:, :k]
+    elif metric == "inner_product":
+        full = a @ b.T
+        order = np.argsort(-full, axis=1, kind="stable")[:, :k]
+    else:
+        full = 1 - (a @ b.T) / (np.linalg.norm(a, axis=1)[:, None] * np.linalg.norm(b, axis=1)[None, :])
+        order = np.argsort(full, axis=1, kind="stable")[:, :k]
+    ref = np.take_along_axis(full, order, axis=1)
+    assert oracle.knn_match(idx, dist, order, ref, eps=1e-4) == 0
+
+
+def test_knn_fewer_rows_than_k():
+    ds = np.eye(3, dtype=np.float32)
+    dist, idx = oracle.knn(ds, ds[:1], 5)
+    assert idx[0, :3].tolist() == [0, 1, 2] and idx[0, 3:].tolist() == [-1, -1]
+
+
+def test_select_k_ties_and_padding():
+    v = np.array([[3, 1, 1, 2, 1], [5, 4, 3, 2, 1]], np.float32)
+    ov, oi = oracle.select_k(v, 3, True)
+    assert oi.tolist() == [[1, 2, 4], [4, 3, 2]]
+    ov, oi = oracle.select_k(v, 2, False)
+    assert oi.tolist() == [[0, 3], [0, 1]]
+    ov, oi = oracle.select_k(v[:, :2], 4, True)
+    assert oi[0].tolist() == [1, 0, -1, -1]
+
+
+def test_pq_packing_roundtrip():
+    rng = np.random.default_rng(0)
+    for bits in (4, 5, 6, 7, 8):
+        codes = rng.integers(0, 1 << bits, (70, 24), dtype=np.uint8)
+        packed = oracle.pack_pq_interleaved(codes, bits)
+        assert packed.shape == (3, -(-24 // (128 // bits)), 32, 16)
+        back = oracle.unpack_pq_interleaved(packed, 70, 24, bits)
+        assert (back == codes).all()
+    # 8-bit: code j of vector v is simply byte j%16 of chunk j/16
+    codes = rng.integers(0, 256, (33, 32), dtype=np.uint8)
+    packed = oracle.pack_pq_interleaved(codes, 8)
+    assert packed[1, 1, 0, 5] == codes[32, 21]
+
+
+def test_ivf_flat_interleave_layout():
+    rows = np.arange(40 * 8, dtype=np.float32).reshape(40, 8)
+    flat = oracle.interleave_ivf_flat(rows)
+    veclen = 4
+    for r, k in [(0, 0), (5, 3), (5, 4), (33, 7)]:
+        off = (r // 32) * 32 * 8 + (k // veclen) * 32 * veclen + (r % 32) * veclen + k % veclen
+        assert flat[off] == rows[r, k]
