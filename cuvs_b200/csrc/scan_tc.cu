@@ -1,0 +1,386 @@
+// tcgen05 scan + fused top-k' kernel for sm_100a.
+//
+// Replaces, on B200, the reference's SIMT distance+select kernels
+//   fusedL2kNN                cpp/src/neighbors/detail/fused_l2_knn.cuh:186-508   (fp32 FFMA tile + WarpSelect)
+//   interleaved_scan (dense)  cpp/src/neighbors/ivf_flat/detail/jit_lto_kernels/interleaved_scan_impl.cuh:70-206
+//   coarse GEMM + select_k    cpp/src/neighbors/ivf_pq/ivf_pq_search.cuh:60-168
+//   unfused distance-NN       cpp/src/distance/unfused_distance_nn.cuh:54-118
+// with one warp-specialised persistent kernel:
+//
+//   warp 0   TMA producer : query tile (A, resident per work item) + dataset k-blocks (B ring)
+//   warp 1   MMA issuer   : tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), 128x128 tiles,
+//                           split-bf16 products hi*hi + lo*hi + hi*lo  (passes = 3) or hi*hi (passes = 1)
+//   warps 2-5 epilogue    : tcgen05.ld one accumulator row per thread, s = hn[col] - acc, compare with
+//                           the thread's running k'-th best, rare inserts go through a per-thread smem
+//                           queue and are merged into a sorted register list warp-convergently.
+//
+// The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps
+// the MMAs of tile t+1.  Nothing but the k' (score, position) pairs per query row ever leaves the SM:
+// the n x nq distance matrix of the reference's unfused path (n*nq*4 bytes through HBM) is never
+// materialised.
+#include "common.hpp"
+#include "ptx_sm100.cuh"
+#include "scan_tc.cuh"
+
+#include <cuda.h>
+
+#include <cmath>
+#include <mutex>
+
+namespace b200 {
+namespace {
+
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kQueue     = 40;         // per-thread pending-insert queue (flushed when > kQueue-32 before a 32-col chunk)
+constexpr int kThreads   = 192;
+
+template <int KB, int NPL>
+struct cfg {
+  static constexpr int stages      = NPL == 2 ? 3 : 6;
+  static constexpr int a_bytes     = NPL * KB * kTileBytes;
+  static constexpr int stage_bytes = NPL * kTileBytes;
+  static constexpr int n_bars      = 2 * stages + 2 + 4;
+  static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + stages * stage_bytes + 2 * 128 * 4 /*hn*/ +
+                                 kQueue * 128 * 8 /*queues*/ + n_bars * 8 + 16;
+};
+
+template <int KB, int NPL, int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const float* __restrict__ hn, const tc_item* __restrict__ items, int n_items,
+               float* __restrict__ out_score, uint32_t* __restrict__ out_pos, int64_t out_row_stride)
+{
+  using C = cfg<KB, NPL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA   = base;
+  uint8_t* sB   = sA + C::a_bytes;
+  float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);
+  float* qv     = sHn + 2 * 128;
+  uint32_t* qi  = reinterpret_cast<uint32_t*>(qv + kQueue * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qi + kQueue * 128);
+  uint64_t* full    = bars;
+  uint64_t* empty   = bars + C::stages;
+  uint64_t* a_full  = bars + 2 * C::stages;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* tfull   = a_empty + 1;  // [2]
+  uint64_t* tempty  = tfull + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA_hi);
+    ptx::prefetch_tmap(&tmB_hi);
+    if (NPL == 2) {
+      ptx::prefetch_tmap(&tmA_lo);
+      ptx::prefetch_tmap(&tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc<256>(tmem_slot); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const tc_item item = items[it];
+        ptx::mbar_wait(a_empty, a_phase ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::tma_load_2d(sA + (0 * KB + kb) * kTileBytes, &tmA_hi, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
+          if (NPL == 2)
+            ptx::tma_load_2d(sA + (1 * KB + kb) * kTileBytes, &tmA_lo, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
+        }
+        a_phase ^= 1;
+        for (uint32_t t = 0; t < item.n_tiles; ++t) {
+          const int32_t brow = static_cast<int32_t>(item.b_row0 + t * 128);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[stage], C::stage_bytes);
+            uint8_t* dst = sB + stage * C::stage_bytes;
+            ptx::tma_load_2d(dst, &tmB_hi, &full[stage], kb * 64, brow);
+            if (NPL == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
+            if (++stage == C::stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+      const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint32_t n_tiles = items[it].n_tiles;
+        ptx::mbar_wait(a_full, a_phase);
+        ptx::tc_fence_after_sync();
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+          ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * 128;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t bs = b_addr + stage * C::stage_bytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_hi = ptx::make_smem_desc_sw128(a_addr + (0 * KB + kb) * kTileBytes + k * 32);
+              const uint64_t b_hi = ptx::make_smem_desc_sw128(bs + k * 32);
+              ptx::mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (NPL == 2) {
+                const uint64_t a_lo = ptx::make_smem_desc_sw128(a_addr + (1 * KB + kb) * kTileBytes + k * 32);
+                const uint64_t b_lo = ptx::make_smem_desc_sw128(bs + kTileBytes + k * 32);
+                ptx::mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
+                ptx::mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+              }
+            }
+            ptx::mma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
+            if (++stage == C::stages) { stage = 0; phase ^= 1; }
+          }
+          ptx::mma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
+        a_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 1 row per thread)
+    const int quarter = warp & 3;             // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int row     = quarter * 32 + lane;  // accumulator row == query row within the tile
+    uint32_t acc = 0, acc_phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const tc_item item = items[it];
+      float lv[KC];
+      uint32_t li[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) { lv[j] = INFINITY; li[j] = 0xffffffffu; }
+      float thr = INFINITY;
+      int cnt   = 0;
+
+      auto flush = [&]() {
+        for (int e = 0; e < cnt; ++e) {
+          const float s    = qv[e * 128 + row];
+          const uint32_t p = qi[e * 128 + row];
+          if (s < lv[KC - 1]) {
+#pragma unroll
+            for (int j = KC - 1; j > 0; --j) {
+              if (s < lv[j - 1]) { lv[j] = lv[j - 1]; li[j] = li[j - 1]; }
+              else if (s < lv[j]) { lv[j] = s; li[j] = p; }
+            }
+            if (s < lv[0]) { lv[0] = s; li[0] = p; }
+          }
+        }
+        cnt = 0;
+        thr = lv[KC - 1];
+      };
+
+      const float* hn_item = hn + item.b_row0;
+      float hn_reg         = item.n_tiles ? hn_item[row] : 0.f;
+      for (uint32_t t = 0; t < item.n_tiles; ++t) {
+        sHn[acc * 128 + row] = hn_reg;
+        ptx::named_bar_sync(1, 128);
+        if (t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t pos0 = item.b_row0 + t * 128;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          if (__any_sync(0xffffffffu, cnt > kQueue - 32)) flush();
+          __syncwarp();
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + ch * 32, v);
+          ptx::tmem_ld_wait();
+          const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + ch * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 h = h4[c4];
+            const float s0 = h.x - __uint_as_float(v[c4 * 4 + 0]);
+            const float s1 = h.y - __uint_as_float(v[c4 * 4 + 1]);
+            const float s2 = h.z - __uint_as_float(v[c4 * 4 + 2]);
+            const float s3 = h.w - __uint_as_float(v[c4 * 4 + 3]);
+            const uint32_t p = pos0 + ch * 32 + c4 * 4;
+            if (s0 < thr) { qv[cnt * 128 + row] = s0; qi[cnt * 128 + row] = p + 0; ++cnt; }
+            if (s1 < thr) { qv[cnt * 128 + row] = s1; qi[cnt * 128 + row] = p + 1; ++cnt; }
+            if (s2 < thr) { qv[cnt * 128 + row] = s2; qi[cnt * 128 + row] = p + 2; ++cnt; }
+            if (s3 < thr) { qv[cnt * 128 + row] = s3; qi[cnt * 128 + row] = p + 3; ++cnt; }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      flush();
+      if (static_cast<uint32_t>(row) < item.valid_rows) {
+        float* os    = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride;
+        uint32_t* op = out_pos + item.out_off + static_cast<int64_t>(row) * out_row_stride;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) { os[j] = lv[j]; op[j] = li[j]; }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { ptx::tmem_dealloc<256>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------ host side
+using encode_fn_t = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t get_encode_fn()
+{
+  static encode_fn_t fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_fn_t>(p);
+  });
+  B2_EXPECTS(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+CUtensorMap make_plane_map(const __nv_bfloat16* ptr, int64_t rows, int Kp)
+{
+  CUtensorMap m;
+  cuuint64_t gdim[2]    = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Kp) * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2]     = {64, 128};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_EXPECTS(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rows=%lld Kp=%d)", int(r), (long long)rows, Kp);
+  return m;
+}
+
+template <int KB, int NPL, int KC>
+void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+            const CUtensorMap& b_lo, const float* hn, const tc_item* items, int n_items, float* out_score,
+            uint32_t* out_pos, int64_t out_row_stride)
+{
+  auto kern = tc_scan_kernel<KB, NPL, KC>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg<KB, NPL>::smem)));
+    attr_set = true;
+  }
+  int grid = n_items < sm_count ? n_items : sm_count;
+  kern<<<grid, kThreads, cfg<KB, NPL>::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, out_score, out_pos,
+                                                        out_row_stride);
+  B2_CUDA(cudaGetLastError());
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ x, int64_t n, int64_t ld, int d, int Kp,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t rows_pad,
+                                    const float* __restrict__ row_scale)
+{
+  const int64_t total = rows_pad * (Kp / 2);
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = t / (Kp / 2);
+    const int c     = static_cast<int>(t % (Kp / 2)) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < n) {
+      const float sc = row_scale ? row_scale[r] : 1.0f;
+      if (c < d) v0 = x[r * ld + c] * sc;
+      if (c + 1 < d) v1 = x[r * ld + c + 1] * sc;
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    reinterpret_cast<__nv_bfloat162*>(hi)[t] = __nv_bfloat162(h0, h1);
+    if (lo) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      reinterpret_cast<__nv_bfloat162*>(lo)[t] = __nv_bfloat162(l0, l1);
+    }
+  }
+}
+
+__global__ void half_norms_kernel(const float* __restrict__ xn, int64_t n, int64_t rows_pad, float* __restrict__ hn)
+{
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= rows_pad) return;
+  hn[i] = i < n ? (xn ? 0.5f * xn[i] : 0.0f) : INFINITY;
+}
+
+}  // namespace
+
+bool tc_supported(int device, int d)
+{
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return false;
+  return major == 10 && d >= 1 && tc_pad_k(d) <= 128;
+}
+
+void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld, int d, int Kp, __nv_bfloat16* hi,
+                     __nv_bfloat16* lo, int64_t rows_pad, const float* row_scale)
+{
+  if (rows_pad == 0) return;
+  int64_t total = rows_pad * (Kp / 2);
+  int blocks    = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  split_planes_kernel<<<blocks, 256, 0, stream>>>(x, n, ld, d, Kp, hi, lo, rows_pad, row_scale);
+  B2_CUDA(cudaGetLastError());
+}
+
+void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn)
+{
+  if (rows_pad == 0) return;
+  half_norms_kernel<<<static_cast<unsigned>((rows_pad + 255) / 256), 256, 0, stream>>>(xn, n, rows_pad, hn);
+  B2_CUDA(cudaGetLastError());
+}
+
+void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
+                  int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
+                  const float* hn, const tc_item* items_dev, int n_items, int KC, int passes, float* out_score,
+                  uint32_t* out_pos, int64_t out_row_stride)
+{
+  if (n_items == 0) return;
+  B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
+  B2_EXPECTS(KC == 16 || KC == 32, "tc_scan_topk: KC must be 16 or 32");
+  B2_EXPECTS(passes == 1 || passes == 3, "tc_scan_topk: passes must be 1 or 3");
+  B2_EXPECTS(passes == 1 || (a_lo && b_lo), "tc_scan_topk: lo planes required for 3-pass mode");
+  const int sms = sm_count_of(device);
+  CUtensorMap mA  = make_plane_map(a_hi, a_rows_pad, Kp);
+  CUtensorMap mB  = make_plane_map(b_hi, b_rows_pad, Kp);
+  CUtensorMap mAl = passes == 3 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
+  CUtensorMap mBl = passes == 3 ? make_plane_map(b_lo, b_rows_pad, Kp) : mB;
+#define B2_TC_CASE(KB_, NPL_, KC_)                                                                                     \
+  if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
+    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, out_score, out_pos, out_row_stride);
+  B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32)
+  B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32)
+#undef B2_TC_CASE
+  B2_FAIL("tc_scan_topk: no kernel for Kp=%d passes=%d KC=%d", Kp, passes, KC);
+}
+
+}  // namespace b200

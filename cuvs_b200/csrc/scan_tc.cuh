@@ -1,0 +1,53 @@
+// Tensor-core scan + fused top-k engine (host API).
+//
+// One kernel serves every dense "queries x rows -> k best rows per query" contraction of the hot
+// path: brute force (a3 in SURVEY §8a), IVF coarse search (a7/a10), IVF-Flat list scans (a8), the
+// k-means assignment step (a18).  Scores are  s(q, x) = hn[x] - q.x  (hn = |x|^2/2 for L2, 0 for
+// inner product, +inf for padding rows), smaller is better; the caller maps them back to the
+// metric.  See scan_tc.cu for the kernel and DESIGN.md §3 for the layout.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b200 {
+
+constexpr int kTcTile = 128;  // rows of A (queries) and rows of B (dataset) per MMA tile
+
+/** One unit of work: 128 query rows against a contiguous range of 128-row dataset tiles. */
+struct tc_item {
+  uint32_t a_row0;      // first row in the A planes (multiple of 128)
+  uint32_t b_row0;      // first row in the B planes (multiple of 128)
+  uint32_t n_tiles;     // number of 128-row B tiles to scan
+  uint32_t valid_rows;  // rows of the A tile that are real queries (<= 128)
+  uint64_t out_off;     // element offset of (row 0, slot 0) in out_score/out_pos
+};
+
+inline int tc_pad_k(int d) { return (d + 63) / 64 * 64; }
+inline int64_t tc_pad_rows(int64_t n) { return (n + kTcTile - 1) / kTcTile * kTcTile; }
+
+/** True when the device/shape combination is served by the tcgen05 kernel (sm_100, Kp <= 128). */
+bool tc_supported(int device, int d);
+
+/**
+ * Split an fp32 row-major matrix into bf16 hi / lo planes [rows_pad, Kp] (x ~= hi + lo, zero padded).
+ * `scale` multiplies each row first when non-null (1/|x| for cosine).  lo may be null (hi only).
+ */
+void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld, int d, int Kp, __nv_bfloat16* hi,
+                     __nv_bfloat16* lo, int64_t rows_pad, const float* row_scale);
+
+/** hn[j] = 0.5 * xn[j] (or 0 when xn == null) for j < n, +inf for n <= j < rows_pad. */
+void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn);
+
+/**
+ * Run the scan.  For every item and every valid row r the kernel writes KC (score, position)
+ * pairs, sorted best-first, at out_off + r * out_row_stride (+0..KC-1); empty slots hold
+ * (+inf, 0xffffffff).  `passes` = 3 uses hi*hi + lo*hi + hi*lo (fp32-grade products), 1 uses hi*hi.
+ * KC must be 16 or 32.
+ */
+void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
+                  int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
+                  const float* hn, const tc_item* items_dev, int n_items, int KC, int passes, float* out_score,
+                  uint32_t* out_pos, int64_t out_row_stride);
+
+}  // namespace b200
