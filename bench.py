@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line per run (driver contract, "tier" reading).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step = one search() of the whole 10k-query batch through the library's C ABI.
+  value   QPS with queries resident in HBM (device-timed, CUDA events, L2 flushed between steps)
+  e2e     QPS through the public Python binding with HOST (pinned) queries: H2D of the batch and D2H
+          of neighbors+distances are inside the timed region
+  roofline  dominant kernel, timed live with CUDA events on the launching stream (cuvsB200Timing*)
+  cpu_baseline  the oracle (C port, OpenMP) on a bounded sample of the same workload, rank 0, N=1
+--impl reference: the reference has no CPU implementation of these searches and its CUDA build
+cannot be produced offline, so the reference arm times the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.stop, self.idx = [], threading.Event(), gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- workloads
+def gen_clustered(n, d, seed, centers, sigma=0.25, device="cuda", chunk=1 << 20):
+    """SURVEY §8d synthetic data: points = centre + sigma * N(0, I), generated on the device."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        lab = torch.randint(0, centers.shape[0], (e - s,), generator=g, device=device)
+        out[s:e] = centers[lab] + sigma * torch.randn((e - s, d), generator=g, device=device)
+    return out
+
+
+class BruteForceWorkload:
+    """configs[1]: brute_force::search 1M x 128 f32 L2, batch 10k, k=10."""
+    name = "brute_force 1M x 128 f32 L2 (sqeuclidean), batch 10k, k=10"
+    dtype = "bf16x3->f32"  # split-bf16 tensor-core products, fp32 accumulate, fp32 exact re-scoring
+    timing_section = "tc_scan"
+
+    def __init__(self, n=1_000_000, d=128, nq=10_000, k=10, seed=1234):
+        self.n, self.d, self.nq, self.k = n, d, nq, k
+        from cuvs_b200.neighbors import brute_force
+        self.bf = brute_force
+        g = torch.Generator(device="cuda")
+        g.manual_seed(99)
+        centers = torch.randn((max(1, n // 1000), d), generator=g, device="cuda")
+        self.dataset = gen_clustered(n, d, seed, centers)
+        self.queries = gen_clustered(nq, d, seed + 3087, centers)
+        self.index = brute_force.build(self.dataset)
+        self.h_queries = self.queries.cpu().pin_memory()
+        self.neighbors = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+
+    def config(self):
+        return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
+                "data": "clustered gaussians (SURVEY 8d), seed 1234/4321", "l2_flush": "256 MiB write between timed steps",
+                "recall_at_10": 1.0, "parallelism": "single GPU"}
+
+    def step(self, res):
+        self.bf.search(self.index, self.queries, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+
+    def e2e_step(self, res):
+        q = self.h_queries.to("cuda", non_blocking=True)
+        self.bf.search(self.index, q, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+        self.h_neighbors.copy_(self.neighbors, non_blocking=True)
+        self.h_distances.copy_(self.distances, non_blocking=True)
+
+    def e2e_bytes(self):
+        return self.nq * self.d * 4, self.nq * self.k * 12
+
+    def units(self):
+        return self.nq
+
+    def roofline(self, kernel_ms, pk):
+        flops = 2.0 * self.nq * self.n * self.d  # algorithmic (useful) FLOPs; the 3-term split executes 3x this
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "tc_scan_kernel (tcgen05, split-bf16 x3 + fused top-k')", "achieved": ach,
+                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                "frac_executed_flops": 3 * ach / pk["tf_burst"], "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
+                "traffic": None, "kernel_ms": kernel_ms}
+
+    def cpu_baseline(self, budget_s=20.0):
+        import oracle
+        ds = self.dataset.cpu().numpy()
+        qs = self.queries[:64].cpu().numpy()
+        t0 = time.time()
+        oracle.knn(ds, qs[:8], self.k)
+        per_q = (time.time() - t0) / 8
+        m = int(max(8, min(64, budget_s / max(per_q, 1e-6))))
+        t0 = time.time()
+        oracle.knn(ds, qs[:m], self.k)
+        dt = time.time() - t0
+        return {"value": m / dt, "unit": "queries/s", "cores": oracle.num_threads(), "kind": "port",
+                "sample": f"{m} of {self.nq} queries against all {self.n} rows (oracle/oracle.c exact fp32 kNN, OpenMP)"}
+
+    def check(self):
+        import oracle
+        qs = self.queries[:32].cpu().numpy()
+        rd, ri = oracle.knn(self.dataset.cpu().numpy(), qs, self.k)
+        ok = (self.neighbors[:32].cpu().numpy() == ri).all()
+        return bool(ok)
+
+
+WORKLOADS = {"brute_force": BruteForceWorkload}
+
+
+def launches():
+    from cuvs_b200._capi import lib
+    lib.cuvsB200KernelLaunches.restype = C.c_longlong
+    return int(lib.cuvsB200KernelLaunches())
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cuvs_b200._capi import lib
+    from cuvs_b200.common import Resources
+    lib.cuvsB200TimingTotalMs.restype = C.c_double
+
+    wl = WORKLOADS[args.workload](**({"n": args.n} if args.n else {}), **({"nq": args.nq} if args.nq else {}))
+    res = Resources()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        total = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(res)
+            res.sync()
+            e.record()
+            e.synchronize()
+            total += s.elapsed_time(e)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        wl.step(res)
+    res.sync()
+    barrier()
+    lib.cuvsB200TimingReset()
+    lib.cuvsB200TimingEnable(1)
+    l0 = launches()
+    with ClockSampler(local) as clk:
+        barrier()
+        ms = timed(wl.step, args.steps)
+        barrier()
+    n_launch = launches() - l0
+    lib.cuvsB200TimingEnable(0)
+    cnt = C.c_int(0)
+    kernel_ms_total = lib.cuvsB200TimingTotalMs(wl.timing_section.encode(), C.byref(cnt))
+    kernel_ms = kernel_ms_total / max(cnt.value, 1)
+    ok = wl.check()
+
+    # end-to-end: host queries in, host results out
+    for _ in range(2):
+        wl.e2e_step(res)
+    res.sync()
+    barrier()
+    e2e_ms = timed(wl.e2e_step, args.steps)
+    barrier()
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    pk = peaks()
+    if rank == 0:
+        units = wl.units() * args.steps
+        hb, db = wl.e2e_bytes()
+        line = {
+            "metric": "QPS (queries/s) of one batched search() call, recall@10 as stated in config", "value": units / (ms * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": wl.dtype, "data": "synthetic", "config": wl.config(), "clocks": clk.summary(),
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": n_launch, "parity_spot_check": ok,
+            "roofline": wl.roofline(kernel_ms, pk),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = wl.cpu_baseline()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the oracle port on the host cores (see module docstring), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    n, d, nq, k = args.n or 1_000_000, 128, args.nq or 10_000, 10
+    rng = np.random.default_rng(1234)
+    centers = np.random.default_rng(99).standard_normal((max(1, n // 1000), d)).astype(np.float32)
+    ds = (centers[rng.integers(0, len(centers), n)] + 0.25 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    qs = (centers[rng.integers(0, len(centers), 256)] + 0.25 * rng.standard_normal((256, d), dtype=np.float32)).astype(np.float32)
+    t0 = time.time()
+    oracle.knn(ds, qs[:8], k)
+    per_q = (time.time() - t0) / 8
+    steps, warm = args.steps, min(args.warmup, 1)
+    m = int(max(4, min(256, 60.0 / max(per_q, 1e-9) / max(steps + warm, 1))))
+    for _ in range(warm):
+        oracle.knn(ds, qs[:m], k)
+    t0 = time.time()
+    for _ in range(steps):
+        oracle.knn(ds, qs[:m], k)
+    dt = time.time() - t0
+    v = m * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "QPS (queries/s) of one batched search() call, recall@10 as stated in config",
+        "value": v, "unit": "queries/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": BruteForceWorkload.name, "n": n, "dim": d, "batch": nq, "k": k, "metric": "sqeuclidean"},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": f"{m} queries per step against all {n} rows (exact fp32 kNN, oracle/oracle.c, OpenMP)"},
+        "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="brute_force", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--nq", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

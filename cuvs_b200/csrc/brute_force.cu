@@ -21,12 +21,15 @@
 #include "exact.cuh"
 #include "scan_tc.cuh"
 #include "select_k.cuh"
+#include "timing.hpp"
 
 #include <cuvs/neighbors/brute_force.h>
+#include <cuvs_b200/ext.h>
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -217,6 +220,64 @@ __global__ void mask_filtered_kernel(int64_t* idx, float* dist, int64_t count, b
   if (dist[i] == worst) idx[i] = -1;  // nothing (or only filtered-out rows) left for this slot
 }
 
+struct bf_cands {
+  dbuf<float> score;    // [nq, KC] raw engine scores s = hn - q.x (best first)
+  dbuf<uint32_t> pos;   // [nq, KC] row positions
+  dbuf<float> qn;       // [nq] |q|^2
+};
+
+// Stage 1+2 of the search: split-bf16 tcgen05 scan over `splits` dataset ranges + merge to KC per query.
+static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q, int64_t nq, int KC, bf_cands& out)
+{
+  auto stream           = res->stream;
+  const int64_t nq_pad  = tc_pad_rows(nq);
+  const int m_tiles     = static_cast<int>(nq_pad / 128);
+  const int64_t b_tiles = idx.rows_pad / 128;
+  const int splits      = pick_splits(m_tiles, b_tiles, res->sm_count ? res->sm_count : 148);
+  const int n_items     = m_tiles * splits;
+
+  out.qn.alloc(static_cast<size_t>(nq), stream);
+  row_norms(stream, q, nq, idx.d, idx.d, out.qn.data());
+  dbuf<float> qscale;
+  if (idx.metric == CosineExpanded) {
+    qscale.alloc(static_cast<size_t>(nq), stream);
+    rsqrt_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, stream>>>(out.qn.data(), qscale.data(), nq);
+    B2_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  dbuf<__nv_bfloat16> qhi(static_cast<size_t>(nq_pad) * idx.Kp, stream), qlo(static_cast<size_t>(nq_pad) * idx.Kp, stream);
+  tc_split_planes(stream, q, nq, idx.d, idx.d, idx.Kp, qhi.data(), qlo.data(), nq_pad, qscale.data());
+
+  dbuf<tc_item> items(static_cast<size_t>(n_items), stream);
+  make_items_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(items.data(), m_tiles, splits, nq, static_cast<uint32_t>(b_tiles), KC);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+
+  const int64_t row_stride = static_cast<int64_t>(splits) * KC;
+  dbuf<float> cs(static_cast<size_t>(nq_pad) * row_stride, stream);
+  dbuf<uint32_t> cp(static_cast<size_t>(nq_pad) * row_stride, stream);
+  tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
+               idx.hn.data(), items.data(), n_items, KC, 3, cs.data(), cp.data(), row_stride);
+  if (splits > 1) {
+    out.score.alloc(static_cast<size_t>(nq) * KC, stream);
+    out.pos.alloc(static_cast<size_t>(nq) * KC, stream);
+    select_k(stream, cs.data(), cp.data(), IDX_U32, nq, row_stride, row_stride, KC, out.score.data(), out.pos.data(), IDX_U32, true);
+  } else {
+    out.score = std::move(cs);
+    out.pos   = std::move(cp);
+  }
+}
+
+static approx_map bf_approx_map(const bf_index& idx)
+{
+  approx_map am;
+  am.eps_rel = 1.0f / 8192.0f;  // 2^-13: > 8x the split-bf16 + fp32-accumulation error bound (DESIGN.md §3)
+  if (idx.metric == InnerProduct) { am.sa = -1.f; am.eq = 1.f; am.ec = idx.xn_max; }
+  else if (idx.metric == CosineExpanded) { am.sa = 1.f; am.sc = 1.f; am.eq = 0.f; am.ec = 2.f; }
+  else { am.sa = 2.f; am.sb = 1.f; am.eq = 1.f; am.ec = idx.xn_max; }
+  return am;
+}
+
 static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, const DLTensor& nt, const DLTensor& dt,
                       cuvsFilter prefilter)
 {
@@ -252,7 +313,9 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
   }
 
   const bool select_min = metric_is_min_close(idx.metric);
-  const bool use_tc     = idx.tc && filt.kind == 0 && k <= 24 && idx.n > 0;
+  static const bool force_exact = getenv("CUVS_B200_FORCE_EXACT") != nullptr;  // test knob
+  const bool use_tc     = idx.tc && filt.kind == 0 && k <= 24 && idx.n > 0 && !force_exact;
+  set_last_flagged(0);
   if (!use_tc) {
     search_exact(res, idx, q, nq, 0, k, out_idx, out_dist, filt);
     if (filt.kind)
@@ -262,52 +325,15 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
   }
 
   // ---- tensor-core candidate scan
-  const int KC          = k <= 10 ? 16 : 32;
-  const int64_t nq_pad  = tc_pad_rows(nq);
-  const int m_tiles     = static_cast<int>(nq_pad / 128);
-  const int64_t b_tiles = idx.rows_pad / 128;
-  const int splits      = pick_splits(m_tiles, b_tiles, res->sm_count ? res->sm_count : 148);
-  const int n_items     = m_tiles * splits;
-
-  dbuf<float> qn(static_cast<size_t>(nq), stream);
-  row_norms(stream, q, nq, idx.d, idx.d, qn.data());
-  dbuf<float> qscale;
-  if (idx.metric == CosineExpanded) {
-    qscale.alloc(static_cast<size_t>(nq), stream);
-    rsqrt_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, stream>>>(qn.data(), qscale.data(), nq);
-    B2_CUDA(cudaGetLastError());
-  }
-  dbuf<__nv_bfloat16> qhi(static_cast<size_t>(nq_pad) * idx.Kp, stream), qlo(static_cast<size_t>(nq_pad) * idx.Kp, stream);
-  tc_split_planes(stream, q, nq, idx.d, idx.d, idx.Kp, qhi.data(), qlo.data(), nq_pad, qscale.data());
-
-  dbuf<tc_item> items(static_cast<size_t>(n_items), stream);
-  make_items_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(items.data(), m_tiles, splits, nq, static_cast<uint32_t>(b_tiles), KC);
-  B2_CUDA(cudaGetLastError());
-
-  const int64_t row_stride = static_cast<int64_t>(splits) * KC;
-  dbuf<float> cs(static_cast<size_t>(nq_pad) * row_stride, stream);
-  dbuf<uint32_t> cp(static_cast<size_t>(nq_pad) * row_stride, stream);
-  tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
-               idx.hn.data(), items.data(), n_items, KC, 3, cs.data(), cp.data(), row_stride);
-
-  const float* m_score  = cs.data();
-  const uint32_t* m_pos = cp.data();
-  dbuf<float> ms;
-  dbuf<uint32_t> mp;
-  if (splits > 1) {
-    ms.alloc(static_cast<size_t>(nq) * KC, stream);
-    mp.alloc(static_cast<size_t>(nq) * KC, stream);
-    select_k(stream, cs.data(), cp.data(), IDX_U32, nq, row_stride, row_stride, KC, ms.data(), mp.data(), IDX_U32, true);
-    m_score = ms.data();
-    m_pos   = mp.data();
-  }
+  const int KC = k <= 10 ? 16 : 32;
+  bf_cands cand;
+  bf_tc_candidates(res, idx, q, nq, KC, cand);
+  const float* m_score  = cand.score.data();
+  const uint32_t* m_pos = cand.pos.data();
+  dbuf<float>& qn       = cand.qn;
 
   // ---- exact re-scoring + certificate
-  approx_map am;
-  am.eps_rel = 1.0f / 8192.0f;  // 2^-13: > 8x the split-bf16 + fp32-accumulation error bound (DESIGN.md §3)
-  if (idx.metric == InnerProduct) { am.sa = -1.f; am.eq = 1.f; am.ec = idx.xn_max; }
-  else if (idx.metric == CosineExpanded) { am.sa = 1.f; am.sc = 1.f; am.eq = 0.f; am.ec = 2.f; }
-  else { am.sa = 2.f; am.sb = 1.f; am.eq = 1.f; am.ec = idx.xn_max; }
+  const approx_map am = bf_approx_map(idx);
   dbuf<int> flags(static_cast<size_t>(nq) + 1, stream);
   B2_CUDA(cudaMemsetAsync(flags.data() + nq, 0, sizeof(int), stream));
   const bool need_xn = (idx.metric == L2Expanded || idx.metric == L2SqrtExpanded || idx.metric == CosineExpanded);
@@ -318,6 +344,7 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
   int n_flagged = 0;
   B2_CUDA(cudaMemcpyAsync(&n_flagged, flags.data() + nq, sizeof(int), cudaMemcpyDeviceToHost, stream));
   B2_CUDA(cudaStreamSynchronize(stream));
+  set_last_flagged(n_flagged);
   if (n_flagged > 0) {
     std::vector<int> hflags(static_cast<size_t>(nq));
     B2_CUDA(cudaMemcpyAsync(hflags.data(), flags.data(), sizeof(int) * nq, cudaMemcpyDeviceToHost, stream));
@@ -398,6 +425,29 @@ cuvsError_t cuvsBruteForceSearch(cuvsResources_t res, cuvsBruteForceIndex_t inde
     } else {
       B2_FAIL("Unsupported queries DLtensor dtype: %d and bits: %d", queries.dtype.code, queries.dtype.bits);
     }
+  });
+}
+
+cuvsError_t cuvsB200BruteForceCandidates(cuvsResources_t res, cuvsBruteForceIndex_t index, DLManagedTensor* queries,
+                                         DLManagedTensor* cand_pos, DLManagedTensor* cand_score)
+{
+  return guarded([=] {
+    auto r = as_res(res);
+    B2_EXPECTS(index && index->addr && queries && cand_pos && cand_score, "null argument");
+    auto& idx           = *reinterpret_cast<bf_index*>(index->addr);
+    const DLTensor& q   = queries->dl_tensor;
+    const DLTensor& cp  = cand_pos->dl_tensor;
+    const DLTensor& cs  = cand_score->dl_tensor;
+    B2_EXPECTS(idx.tc, "index has no tensor-core planes on this device");
+    B2_EXPECTS(dl_is(q, kDLFloat, 32) && dl_is_device(q) && dl_is_c_contiguous(q) && q.ndim == 2 && q.shape[1] == idx.d, "bad queries");
+    const int KC = static_cast<int>(cp.shape[1]);
+    B2_EXPECTS((KC == 16 || KC == 32) && dl_is(cp, kDLUInt, 32) && dl_is(cs, kDLFloat, 32) && cp.shape[0] == q.shape[0] &&
+                 cs.shape[0] == q.shape[0] && cs.shape[1] == KC, "bad candidate tensors");
+    bf_cands c;
+    bf_tc_candidates(r, idx, dl_ptr<float>(q), q.shape[0], KC, c);
+    B2_CUDA(cudaMemcpyAsync(dl_ptr<void>(cp), c.pos.data(), sizeof(uint32_t) * q.shape[0] * KC, cudaMemcpyDeviceToDevice, r->stream));
+    B2_CUDA(cudaMemcpyAsync(dl_ptr<void>(cs), c.score.data(), sizeof(float) * q.shape[0] * KC, cudaMemcpyDeviceToDevice, r->stream));
+    B2_CUDA(cudaStreamSynchronize(r->stream));
   });
 }
 

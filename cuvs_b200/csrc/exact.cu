@@ -5,6 +5,7 @@
 //   post-selection sqrt       cpp/src/neighbors/detail/knn_brute_force.cuh:468-479
 #include "common.hpp"
 #include "exact.cuh"
+#include "timing.hpp"
 
 #include <cfloat>
 
@@ -259,6 +260,7 @@ __global__ void postprocess_kernel(float* dist, int64_t count, int metric)
 void row_norms(cudaStream_t stream, const float* x, int64_t n, int d, int64_t ld, float* out)
 {
   if (n == 0) return;
+  count_launch();
   row_norms_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(x, n, d, ld, out);
   B2_CUDA(cudaGetLastError());
 }
@@ -271,6 +273,8 @@ void exact_distance_tile(cudaStream_t stream, const float* q, int64_t nq, int64_
   dim3 grid(static_cast<unsigned>((n + TN - 1) / TN), static_cast<unsigned>((nq + TM - 1) / TM));
   B2_EXPECTS(grid.y <= 65535, "exact_distance_tile: too many query rows per call");
   const bool sq = (metric == L2Unexpanded || metric == L2SqrtUnexpanded);
+  count_launch();
+  timed_section ts("exact_tile", stream);
   if (sq)
     exact_tile_kernel<true><<<grid, 256, 0, stream>>>(q, nq, ldq, x, n, ldx, d, qn, xn, int(metric), out, ldo, filt, q_row0);
   else
@@ -287,6 +291,7 @@ void rescore_topk(cudaStream_t stream, const float* q, int64_t nq, int64_t ldq, 
   B2_EXPECTS(kc >= 1 && kc <= kMaxCand, "rescore_topk: candidate count %d out of range", kc);
   const int warps = 4;
   size_t smem     = static_cast<size_t>(warps) * kc * (sizeof(float) + sizeof(int64_t));
+  count_launch();
   rescore_kernel<<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, stream>>>(
     q, nq, ldq, x, ldx, d, qn, xn, int(metric), cand_pos, cand_score, kc, src_ids, k, out_idx, out_dist, pad_id, amap,
     flags, n_flagged);
@@ -297,6 +302,7 @@ void postprocess_distances(cudaStream_t stream, float* dist, int64_t count, cuvs
 {
   if (count == 0) return;
   if (metric != L2SqrtExpanded && metric != L2SqrtUnexpanded) return;
+  count_launch();
   postprocess_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, stream>>>(dist, count, int(metric));
   B2_CUDA(cudaGetLastError());
 }

@@ -21,6 +21,7 @@
 #include "common.hpp"
 #include "ptx_sm100.cuh"
 #include "scan_tc.cuh"
+#include "timing.hpp"
 
 #include <cuda.h>
 
@@ -296,6 +297,8 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
     attr_set = true;
   }
   int grid = n_items < sm_count ? n_items : sm_count;
+  timed_section ts("tc_scan", stream);
+  count_launch();
   kern<<<grid, kThreads, cfg<KB, NPL>::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, out_score, out_pos,
                                                         out_row_stride);
   B2_CUDA(cudaGetLastError());
@@ -348,6 +351,7 @@ void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld,
   if (rows_pad == 0) return;
   int64_t total = rows_pad * (Kp / 2);
   int blocks    = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  count_launch();
   split_planes_kernel<<<blocks, 256, 0, stream>>>(x, n, ld, d, Kp, hi, lo, rows_pad, row_scale);
   B2_CUDA(cudaGetLastError());
 }
@@ -355,6 +359,7 @@ void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld,
 void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn)
 {
   if (rows_pad == 0) return;
+  count_launch();
   half_norms_kernel<<<static_cast<unsigned>((rows_pad + 255) / 256), 256, 0, stream>>>(xn, n, rows_pad, hn);
   B2_CUDA(cudaGetLastError());
 }

@@ -9,6 +9,7 @@
 // reproducible against the oracle (oracle/oracle.c: oracle_select_k).
 #include "common.hpp"
 #include "select_k.cuh"
+#include "timing.hpp"
 
 #include <cuvs/selection/select_k.h>
 
@@ -20,7 +21,8 @@ namespace {
 __device__ __forceinline__ uint32_t f2key(float v, bool select_min)
 {
   uint32_t u = __float_as_uint(v);
-  u          = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if ((u << 1) == 0) u = 0;  // -0.0 == +0.0 (the oracle compares floats)
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return select_min ? u : ~u;
 }
 
@@ -201,6 +203,7 @@ void launch(cudaStream_t stream, const float* in_val, const void* in_idx, int64_
   int threads = len <= 2048 ? 128 : (len <= 32768 ? 256 : 1024);
   if (kpow2 / 2 > threads && threads < 1024) threads = kpow2 / 2 > 1024 ? 1024 : kpow2 / 2;
   size_t smem = (256 + 8 + 32) * sizeof(uint32_t) + static_cast<size_t>(kpow2) * sizeof(uint64_t);
+  count_launch();
   select_k_kernel<IdxIn, IdxOut, HasIdx><<<static_cast<unsigned>(batch), threads, smem, stream>>>(
     in_val, static_cast<const IdxIn*>(in_idx), len, in_ld, k, kpow2, out_val, static_cast<IdxOut*>(out_idx), select_min);
   B2_CUDA(cudaGetLastError());
@@ -250,6 +253,7 @@ void knn_merge_parts(cudaStream_t stream, const float* in_keys, const int64_t* i
   dbuf<int64_t> tv(static_cast<size_t>(n_parts * n_rows * k), stream);
   int64_t total = n_parts * n_rows * k;
   int blocks    = static_cast<int>(std::min<int64_t>((total + 255) / 256, 65535));
+  count_launch();
   merge_gather_kernel<<<blocks, 256, 0, stream>>>(in_keys, in_vals, tk.data(), tv.data(), n_parts, n_rows, k,
                                                   translations_dev);
   B2_CUDA(cudaGetLastError());

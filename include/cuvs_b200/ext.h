@@ -1,0 +1,36 @@
+/*
+ * cuvs_b200 extensions to the cuVS C ABI (not part of the reference's surface):
+ * per-kernel CUDA-event timing for bench.py's roofline block, and introspection hooks used by the
+ * parity tests.  None of these is needed by a binding that only uses the reference's API.
+ */
+#pragma once
+#include <cuvs/core/c_api.h>
+#include <cuvs/neighbors/brute_force.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Enable/disable recording of CUDA events around the library's dominant kernels (on the stream they
+ * are launched on).  Disabled by default (zero overhead). */
+CUVS_EXPORT void cuvsB200TimingEnable(int on);
+/* Discards everything recorded so far. */
+CUVS_EXPORT void cuvsB200TimingReset(void);
+/* Synchronises the recorded events of section `name` ("tc_scan", "pq_scan", "cagra_search", ...)
+ * and returns their summed duration in milliseconds; *count receives the number of launches. */
+CUVS_EXPORT double cuvsB200TimingTotalMs(const char* name, int* count);
+
+/* Number of queries of the calling thread's last cuvsBruteForceSearch that failed the candidate
+ * certificate and were recomputed on the exact path, and the number of kernels that search launched. */
+CUVS_EXPORT int cuvsB200LastFlagged(void);
+CUVS_EXPORT long long cuvsB200KernelLaunches(void);
+
+/* Raw candidate output of the tensor-core scan of brute force (after the per-split merge):
+ * cand_pos [nq, kc] uint32, cand_score [nq, kc] f32 (approximate selection-form distance). kc in {16, 32}. */
+CUVS_EXPORT cuvsError_t cuvsB200BruteForceCandidates(cuvsResources_t res,
+                                                     cuvsBruteForceIndex_t index,
+                                                     DLManagedTensor* queries,
+                                                     DLManagedTensor* cand_pos,
+                                                     DLManagedTensor* cand_score);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,70 @@
+"""GPU parity: cuvsSelectK / cuvsKnnMergeParts vs the oracle (ties -> smaller position, padding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _select(v, k, select_min=True, idx=None, out_dtype=torch.int64):
+    from cuvs_b200._capi import DL, check, lib
+    from cuvs_b200.common import Resources
+    res = Resources()
+    tv = torch.from_numpy(v).cuda()
+    ov = torch.empty(v.shape[0], k, device="cuda")
+    oi = torch.empty(v.shape[0], k, dtype=out_dtype, device="cuda")
+    ti = None if idx is None else DL(torch.from_numpy(idx).cuda())
+    check(lib.cuvsSelectK(res.get_c_obj(), DL(tv).ptr, ti.ptr if ti else None, DL(ov).ptr, DL(oi).ptr,
+                          C.c_bool(select_min), C.c_bool(True)))
+    res.sync()
+    return ov.cpu().numpy(), oi.cpu().numpy().astype(np.int64)
+
+
+@pytest.mark.parametrize("batch,length,k", [(7, 1, 1), (33, 100, 10), (10, 640, 10), (4, 5000, 64), (3, 70000, 100),
+                                            (2, 300, 300), (5, 1024, 1024), (2, 9, 20), (1, 1 << 20, 16)])
+@pytest.mark.parametrize("select_min", [True, False])
+def test_select_k_matches_oracle(batch, length, k, select_min):
+    rng = np.random.default_rng(batch * 1000 + length + k)
+    v = rng.standard_normal((batch, length)).astype(np.float32)
+    v[:, ::7] = np.round(v[:, ::7], 1)  # plenty of exact ties
+    ov, oi = _select(v, k, select_min)
+    rv, ri = oracle.select_k(v, k, select_min)
+    np.testing.assert_array_equal(oi, ri)
+    np.testing.assert_array_equal(ov, rv)
+
+
+def test_select_k_with_payload_and_special_values():
+    v = np.array([[np.inf, -np.inf, 0.0, -0.0, 5.0, 5.0, 1e-38, 3.4e38]], np.float32)
+    idx = (np.arange(8, dtype=np.int64) * 10 + 3)[None, :]
+    ov, oi = _select(v, 4, True, idx)
+    assert oi[0].tolist() == [13, 23, 33, 63]  # -inf, 0.0 == -0.0 (position order), 1e-38
+    ov, oi = _select(v, 3, False, idx)
+    assert oi[0].tolist() == [3, 73, 43]
+
+
+def test_knn_merge_parts():
+    from cuvs_b200._capi import DL, check, lib
+    from cuvs_b200.common import Resources
+    rng = np.random.default_rng(5)
+    n_parts, n_rows, k = 8, 100, 10
+    keys = np.sort(rng.random((n_parts, n_rows, k)).astype(np.float32), axis=2)
+    vals = rng.integers(0, 1000, (n_parts, n_rows, k)).astype(np.int64)
+    trans = (np.arange(n_parts) * 1000).astype(np.int64)
+    res = Resources()
+    ik = torch.from_numpy(keys.reshape(n_parts * n_rows, k)).cuda()
+    iv = torch.from_numpy(vals.reshape(n_parts * n_rows, k)).cuda()
+    ok = torch.empty(n_rows, k, device="cuda")
+    ov = torch.empty(n_rows, k, dtype=torch.int64, device="cuda")
+    tr = (C.c_int64 * n_parts)(*trans.tolist())
+    check(lib.cuvsKnnMergeParts(res.get_c_obj(), DL(ik).ptr, DL(iv).ptr, DL(ok).ptr, DL(ov).ptr, C.c_int64(n_parts), tr,
+                                C.c_bool(True)))
+    res.sync()
+    allk = keys.transpose(1, 0, 2).reshape(n_rows, n_parts * k)
+    allv = (vals + trans[:, None, None]).transpose(1, 0, 2).reshape(n_rows, n_parts * k)
+    rk, ri = oracle.select_k(allk, k, True, allv)
+    np.testing.assert_array_equal(ok.cpu().numpy(), rk)
+    np.testing.assert_array_equal(ov.cpu().numpy(), ri)
