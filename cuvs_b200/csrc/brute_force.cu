@@ -91,7 +91,7 @@ __global__ void max_kernel(const float* __restrict__ v, int64_t n, float* __rest
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0
 }
 
-__global__ void make_items_kernel(tc_item* items, int m_tiles, int splits, int64_t nq, uint32_t tiles_total, int KC)
+__global__ void make_items_kernel(tc_item* items, int m_tiles, int splits, int64_t nq, uint32_t tiles_total, int KCW)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m_tiles * splits) return;
@@ -105,7 +105,7 @@ __global__ void make_items_kernel(tc_item* items, int m_tiles, int splits, int64
   it.n_tiles    = t1 - t0;
   int64_t valid = nq - static_cast<int64_t>(m) * 128;
   it.valid_rows = valid > 128 ? 128 : static_cast<uint32_t>(valid);
-  it.out_off    = (static_cast<uint64_t>(m) * 128 * splits + s) * KC;
+  it.out_off    = (static_cast<uint64_t>(m) * 128 * splits + s) * KCW;
   items[i]      = it;
 }
 
@@ -249,16 +249,17 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
   tc_split_planes(stream, q, nq, idx.d, idx.d, idx.Kp, qhi.data(), qlo.data(), nq_pad, qscale.data());
 
   dbuf<tc_item> items(static_cast<size_t>(n_items), stream);
-  make_items_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(items.data(), m_tiles, splits, nq, static_cast<uint32_t>(b_tiles), KC);
+  const int KCW = KC * tc_lists_per_item();  // candidates per (item, query row)
+  make_items_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(items.data(), m_tiles, splits, nq, static_cast<uint32_t>(b_tiles), KCW);
   B2_CUDA(cudaGetLastError());
   count_launch();
 
-  const int64_t row_stride = static_cast<int64_t>(splits) * KC;
+  const int64_t row_stride = static_cast<int64_t>(splits) * KCW;
   dbuf<float> cs(static_cast<size_t>(nq_pad) * row_stride, stream);
   dbuf<uint32_t> cp(static_cast<size_t>(nq_pad) * row_stride, stream);
   tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
-               idx.hn.data(), items.data(), n_items, KC, 3, cs.data(), cp.data(), row_stride);
-  if (splits > 1) {
+               idx.hn.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride);
+  if (row_stride > KC) {
     out.score.alloc(static_cast<size_t>(nq) * KC, stream);
     out.pos.alloc(static_cast<size_t>(nq) * KC, stream);
     select_k(stream, cs.data(), cp.data(), IDX_U32, nq, row_stride, row_stride, KC, out.score.data(), out.pos.data(), IDX_U32, true);

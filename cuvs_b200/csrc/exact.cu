@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ 
     worst_approx = select_min ? fmaxf(worst_approx, t) : fminf(worst_approx, t);
   }
   __syncwarp();
-  // rank by (distance, id); ranks are unique because ids are
+  // rank by (distance, id, slot): unique ranks even among empty slots
   float kth = select_min ? FLT_MAX : -FLT_MAX;
   for (int c = lane; c < kc; c += 32) {
     float dv = sd[c];
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ 
     for (int o = 0; o < kc; ++o) {
       float d2 = sd[o];
       int64_t i2 = si[o];
-      bool better = (d2 != dv) ? (select_min ? d2 < dv : d2 > dv) : (i2 < iv);
+      bool better = (d2 != dv) ? (select_min ? d2 < dv : d2 > dv) : ((i2 != iv) ? (i2 < iv) : (o < c));
       rank += better ? 1 : 0;
     }
     if (rank < k) {

@@ -1,0 +1,431 @@
+// Shared IVF / k-means machinery: see ivf_common.cuh.
+#include "ivf_common.cuh"
+
+#include "exact.cuh"
+#include "select_k.cuh"
+#include "timing.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <vector>
+
+namespace b200 {
+namespace {
+
+__global__ void iota_items_kernel(tc_item* items, int m_tiles, int64_t n_rows, uint32_t b_tiles, int64_t row_stride)
+{
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= m_tiles) return;
+  tc_item it;
+  it.a_row0     = m * 128;
+  it.b_row0     = 0;
+  it.n_tiles    = b_tiles;
+  int64_t valid = n_rows - static_cast<int64_t>(m) * 128;
+  it.valid_rows = valid > 128 ? 128 : static_cast<uint32_t>(valid);
+  it.out_off    = static_cast<uint64_t>(m) * 128 * row_stride;
+  items[m]      = it;
+}
+
+// best entry among the heads of the `lists` sorted candidate lists of each row
+__global__ void first_of_rows_kernel(const uint32_t* __restrict__ pos, const float* __restrict__ score, int64_t n, int KC,
+                                     int lists, uint32_t* __restrict__ labels, float* __restrict__ out_scores)
+{
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int64_t b = i * KC * lists;
+  float best      = score[b];
+  uint32_t bp     = pos[b];
+  for (int j = 1; j < lists; ++j) {
+    float s    = score[b + j * KC];
+    uint32_t p = pos[b + j * KC];
+    if (s < best || (s == best && p < bp)) { best = s; bp = p; }
+  }
+  labels[i] = bp;
+  if (out_scores) out_scores[i] = best;
+}
+
+// ---- probe bucketing -----------------------------------------------------------------------
+__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, uint32_t* __restrict__ counts)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= total) return;
+  uint32_t l = probes[t];
+  if (l != 0xffffffffu) atomicAdd(&counts[l], 1u);
+}
+
+// single CTA: exclusive scans over lists of (a) pair counts, (b) item counts ceil(cnt/128)
+__global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __restrict__ counts, int64_t n_lists,
+                                                           uint32_t* __restrict__ pair_off, uint32_t* __restrict__ item_off,
+                                                           int* __restrict__ n_items, uint32_t* __restrict__ cursor)
+{
+  __shared__ uint32_t s_pairs[1024], s_items[1024];
+  __shared__ uint32_t run_pairs, run_items;
+  if (threadIdx.x == 0) { run_pairs = 0; run_items = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < n_lists; base += 1024) {
+    int64_t l  = base + threadIdx.x;
+    uint32_t c = l < n_lists ? counts[l] : 0;
+    uint32_t g = (c + 127) / 128;
+    s_pairs[threadIdx.x] = c;
+    s_items[threadIdx.x] = g;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t a = threadIdx.x >= o ? s_pairs[threadIdx.x - o] : 0;
+      uint32_t b = threadIdx.x >= o ? s_items[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_pairs[threadIdx.x] += a;
+      s_items[threadIdx.x] += b;
+      __syncthreads();
+    }
+    if (l < n_lists) {
+      pair_off[l] = run_pairs + s_pairs[threadIdx.x] - c;
+      item_off[l] = run_items + s_items[threadIdx.x] - g;
+      cursor[l]   = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { run_pairs += s_pairs[1023]; run_items += s_items[1023]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_items = static_cast<int>(run_items);
+}
+
+__global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes,
+                                      const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cursor,
+                                      uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_query,
+                                      uint32_t* __restrict__ pair_list)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= total) return;
+  uint32_t l = probes[t];
+  if (l == 0xffffffffu) { slot_of[t] = 0xffffffffu; return; }
+  uint32_t slot    = pair_off[l] + atomicAdd(&cursor[l], 1u);
+  slot_of[t]       = slot;
+  pair_query[slot] = static_cast<uint32_t>(t / n_probes);
+  pair_list[slot]  = l;
+}
+
+__global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ pair_off,
+                                       const uint32_t* __restrict__ item_off, const int64_t* __restrict__ list_offsets,
+                                       int64_t n_lists, int KC, tc_item* __restrict__ items)
+{
+  int64_t l = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (l >= n_lists) return;
+  uint32_t c = counts[l];
+  if (c == 0) return;
+  const uint32_t b_row0  = static_cast<uint32_t>(list_offsets[l]);
+  const uint32_t n_tiles = static_cast<uint32_t>((list_offsets[l + 1] - list_offsets[l]) / 128);
+  uint32_t g = (c + 127) / 128;
+  for (uint32_t j = 0; j < g; ++j) {
+    tc_item it;
+    it.a_row0     = pair_off[l] + j * 128;
+    it.b_row0     = b_row0;
+    it.n_tiles    = n_tiles;
+    it.valid_rows = min(128u, c - j * 128);
+    it.out_off    = static_cast<uint64_t>(it.a_row0) * KC;
+    items[item_off[l] + j] = it;
+  }
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const uint32_t* __restrict__ pair_query, int64_t n_pairs,
+                                   int64_t rows_total, int vec_per_row, uint4* __restrict__ dst)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= rows_total * vec_per_row) return;
+  int64_t r = t / vec_per_row;
+  int v     = static_cast<int>(t % vec_per_row);
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (r < n_pairs) val = src[static_cast<int64_t>(pair_query[r]) * vec_per_row + v];
+  dst[t] = val;
+}
+
+__global__ void gather_cands_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp,
+                                    const uint32_t* __restrict__ slot_of, int64_t total /*nq*n_probes*KC*/, int KC,
+                                    float* __restrict__ out_score, uint32_t* __restrict__ out_pos)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= total) return;
+  int64_t pair = t / KC;
+  int c        = static_cast<int>(t % KC);
+  uint32_t slot = slot_of[pair];
+  float s      = INFINITY;
+  uint32_t p   = 0xffffffffu;
+  if (slot != 0xffffffffu) {
+    s = cs[static_cast<int64_t>(slot) * KC + c];
+    p = cp[static_cast<int64_t>(slot) * KC + c];
+  }
+  out_score[t] = s;
+  out_pos[t]   = p;
+}
+
+// ---- k-means ---------------------------------------------------------------------------------
+__global__ void strided_init_kernel(const float* __restrict__ x, int64_t n, int d, int k, float* __restrict__ centers)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(k) * d) return;
+  int64_t c   = t / d;
+  int64_t row = (c * n) / k;  // evenly spaced rows
+  centers[t]  = x[row * d + (t % d)];
+}
+
+__global__ void accumulate_kernel(const float* __restrict__ x, int64_t n, int d, const uint32_t* __restrict__ labels,
+                                  const float* __restrict__ weights, float* __restrict__ sums, float* __restrict__ counts)
+{
+  // one warp per row; lanes stride over d
+  int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane    = threadIdx.x & 31;
+  if (row >= n) return;
+  uint32_t l = labels[row];
+  float w    = weights ? weights[row] : 1.0f;
+  for (int c = lane; c < d; c += 32) atomicAdd(&sums[static_cast<int64_t>(l) * d + c], w * x[row * d + c]);
+  if (lane == 0) atomicAdd(&counts[l], w);
+}
+
+__global__ void finalize_centers_kernel(const float* __restrict__ sums, const float* __restrict__ counts, int k, int d,
+                                        float* __restrict__ centers)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(k) * d) return;
+  float c = counts[t / d];
+  if (c > 0.f) centers[t] = sums[t] / c;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// one thread per cluster: small clusters jump onto a member of a large cluster
+__global__ void reseed_small_kernel(const float* __restrict__ x, int64_t n, int d, const uint32_t* __restrict__ labels,
+                                    const float* __restrict__ counts, int k, float avg, int iter, float* __restrict__ centers,
+                                    int* __restrict__ n_reseeded)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  if (counts[c] >= 0.25f * avg) return;
+  for (int tries = 0; tries < 64; ++tries) {
+    uint64_t h  = mix64((static_cast<uint64_t>(iter) << 40) ^ (static_cast<uint64_t>(c) << 8) ^ tries);
+    int64_t row = static_cast<int64_t>(h % static_cast<uint64_t>(n));
+    if (counts[labels[row]] >= avg) {
+      // move most of the way to the donor point; keep a little of the donor's centre to break symmetry
+      const float* donor_c = centers + static_cast<int64_t>(labels[row]) * d;
+      for (int j = 0; j < d; ++j) centers[static_cast<int64_t>(c) * d + j] = 0.75f * x[row * d + j] + 0.25f * donor_c[j];
+      atomicAdd(n_reseeded, 1);
+      return;
+    }
+  }
+}
+
+__global__ void sum_scores_kernel(const float* __restrict__ s, const float* __restrict__ xn, int64_t n, double* __restrict__ out)
+{
+  double acc = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float dist = fmaf(2.0f, s[i], xn[i]);  // |x|^2 + 2 (|c|^2/2 - x.c)
+    acc += dist > 0.f ? dist : 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+inline unsigned blocks_for(int64_t n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+}  // namespace
+
+void tc_rows::build(cudaStream_t s, const float* x, int64_t n_, int d_, const float* xn, bool with_lo, const float* row_scale)
+{
+  n = n_; d = d_;
+  Kp       = tc_pad_k(d);
+  rows_pad = tc_pad_rows(std::max<int64_t>(n, 1));
+  hi.alloc(static_cast<size_t>(rows_pad) * Kp);
+  if (with_lo) lo.alloc(static_cast<size_t>(rows_pad) * Kp); else lo.release();
+  hn.alloc(static_cast<size_t>(rows_pad));
+  tc_split_planes(s, x, n, d, d, Kp, hi.data(), with_lo ? lo.data() : nullptr, rows_pad, row_scale);
+  tc_half_norms(s, xn, n, rows_pad, hn.data());
+}
+
+void tc_rows_tmp::build(cudaStream_t s, const float* x, int64_t n_, int d_, bool with_lo, int64_t extra_pad_rows,
+                        const float* row_scale)
+{
+  n = n_; d = d_;
+  Kp       = tc_pad_k(d);
+  rows_pad = tc_pad_rows(std::max<int64_t>(n, 1)) + extra_pad_rows;
+  hi.alloc(static_cast<size_t>(rows_pad) * Kp, s);
+  if (with_lo) lo.alloc(static_cast<size_t>(rows_pad) * Kp, s);
+  tc_split_planes(s, x, n, d, d, Kp, hi.data(), with_lo ? lo.data() : nullptr, rows_pad, row_scale);
+}
+
+void coarse_select(resources* res, const tc_rows_tmp& q, const tc_rows& centers, int n_probes, uint32_t* probes,
+                   float* probe_scores)
+{
+  auto s = res->stream;
+  if (q.n == 0) return;
+  B2_EXPECTS(q.Kp == centers.Kp, "coarse_select: dimension mismatch");
+  const int64_t nq_pad = tc_pad_rows(q.n);
+  const int m_tiles    = static_cast<int>(nq_pad / 128);
+  const int64_t ld     = centers.rows_pad;
+  dbuf<tc_item> items(static_cast<size_t>(m_tiles), s);
+  count_launch();
+  iota_items_kernel<<<blocks_for(m_tiles, 128), 128, 0, s>>>(items.data(), m_tiles, q.n, static_cast<uint32_t>(ld / 128), ld);
+  B2_CUDA(cudaGetLastError());
+  dbuf<float> scores(static_cast<size_t>(nq_pad) * ld, s);
+  const bool three = q.lo.data() != nullptr && centers.lo.data() != nullptr;
+  tc_scan_topk(s, res->device, q.hi.data(), q.lo.data(), q.rows_pad, centers.hi.data(), centers.lo.data(), centers.rows_pad,
+               q.Kp, centers.hn.data(), items.data(), m_tiles, nullptr, 0, three ? 3 : 1, scores.data(), nullptr, ld);
+  dbuf<float> tmp_scores;
+  if (!probe_scores) { tmp_scores.alloc(static_cast<size_t>(q.n) * n_probes, s); probe_scores = tmp_scores.data(); }
+  select_k(s, scores.data(), nullptr, IDX_NONE, q.n, centers.n, ld, n_probes, probe_scores, probes, IDX_U32, true);
+}
+
+void assign_nearest(resources* res, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t n, int64_t x_rows_pad,
+                    int Kp, const tc_rows& centers, uint32_t* labels, float* scores)
+{
+  auto s = res->stream;
+  if (n == 0) return;
+  B2_EXPECTS(Kp == centers.Kp, "assign_nearest: dimension mismatch");
+  const int KC         = 16;
+  const int lists      = tc_lists_per_item();
+  const int KCW        = KC * lists;
+  const int64_t chunk  = int64_t(1) << 20;  // rows per launch: bounds the (score,pos) scratch to 256 MiB
+  const bool three     = x_lo != nullptr && centers.lo.data() != nullptr;
+  dbuf<float> cs(static_cast<size_t>(std::min(chunk, tc_pad_rows(n))) * KCW, s);
+  dbuf<uint32_t> cp(static_cast<size_t>(std::min(chunk, tc_pad_rows(n))) * KCW, s);
+  dbuf<tc_item> items(static_cast<size_t>(std::min(chunk, tc_pad_rows(n)) / 128), s);
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t rows = std::min(chunk, n - r0);
+    const int m_tiles  = static_cast<int>(tc_pad_rows(rows) / 128);
+    count_launch();
+    iota_items_kernel<<<blocks_for(m_tiles, 128), 128, 0, s>>>(items.data(), m_tiles, rows,
+                                                                static_cast<uint32_t>(centers.rows_pad / 128), KCW);
+    B2_CUDA(cudaGetLastError());
+    tc_scan_topk(s, res->device, x_hi + r0 * Kp, x_lo ? x_lo + r0 * Kp : nullptr, x_rows_pad - r0, centers.hi.data(),
+                 centers.lo.data(), centers.rows_pad, Kp, centers.hn.data(), items.data(), m_tiles, nullptr, KC,
+                 three ? 3 : 1, cs.data(), cp.data(), KCW);
+    count_launch();
+    first_of_rows_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(cp.data(), cs.data(), rows, KC, lists, labels + r0,
+                                                               scores ? scores + r0 : nullptr);
+    B2_CUDA(cudaGetLastError());
+  }
+}
+
+void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_probes, int64_t n_lists,
+                   const int64_t* list_offsets_dev, int KC, probe_buckets& out)
+{
+  auto s              = res->stream;
+  const int64_t total = nq * n_probes;
+  out.n_pairs         = total;
+  out.max_items       = static_cast<int>(total / 128 + n_lists + 1);
+  out.slot_of.alloc(static_cast<size_t>(total), s);
+  out.pair_query.alloc(static_cast<size_t>(total), s);
+  out.pair_list.alloc(static_cast<size_t>(total), s);
+  out.items.alloc(static_cast<size_t>(out.max_items), s);
+  out.n_items.alloc(1, s);
+  dbuf<uint32_t> counts(static_cast<size_t>(n_lists), s), pair_off(static_cast<size_t>(n_lists), s),
+    item_off(static_cast<size_t>(n_lists), s), cursor(static_cast<size_t>(n_lists), s);
+  B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * n_lists, s));
+  count_launch(4);
+  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, counts.data());
+  scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), item_off.data(), out.n_items.data(), cursor.data());
+  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, pair_off.data(), cursor.data(),
+                                                                out.slot_of.data(), out.pair_query.data(), out.pair_list.data());
+  make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), item_off.data(),
+                                                                   list_offsets_dev, n_lists, KC, out.items.data());
+  B2_CUDA(cudaGetLastError());
+}
+
+void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, int64_t n_pairs, int64_t rows_total,
+                      int Kp, __nv_bfloat16* dst)
+{
+  const int vec = Kp * 2 / 16;
+  count_launch();
+  gather_rows_kernel<<<blocks_for(rows_total * vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(src), pair_query, n_pairs,
+                                                                        rows_total, vec, reinterpret_cast<uint4*>(dst));
+  B2_CUDA(cudaGetLastError());
+}
+
+void gather_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp, const uint32_t* slot_of, int64_t nq,
+                             int n_probes, int KC, float* out_score, uint32_t* out_pos)
+{
+  const int64_t total = nq * n_probes * KC;
+  if (total == 0) return;
+  count_launch();
+  gather_cands_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cs, cp, slot_of, total, KC, out_score, out_pos);
+  B2_CUDA(cudaGetLastError());
+}
+
+void update_centers(cudaStream_t s, const float* x, int64_t n, int d, const uint32_t* labels, const float* weights, int k,
+                    float* centers, float* sums_ws, float* counts_ws)
+{
+  B2_CUDA(cudaMemsetAsync(sums_ws, 0, sizeof(float) * static_cast<size_t>(k) * d, s));
+  B2_CUDA(cudaMemsetAsync(counts_ws, 0, sizeof(float) * k, s));
+  count_launch(2);
+  accumulate_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(x, n, d, labels, weights, sums_ws, counts_ws);
+  finalize_centers_kernel<<<blocks_for(static_cast<int64_t>(k) * d, 256), 256, 0, s>>>(sums_ws, counts_ws, k, d, centers);
+  B2_CUDA(cudaGetLastError());
+}
+
+void kmeans_train(resources* res, const float* x, int64_t n, int d, int k, int n_iters, float* centers, bool init_from_data,
+                  bool balance, double* inertia, int* iters_done, double tol)
+{
+  auto s = res->stream;
+  B2_EXPECTS(n >= 1 && k >= 1, "kmeans: empty input");
+  B2_EXPECTS(tc_supported(res->device, d), "kmeans: dim %d is not supported by the tensor-core assignment kernel yet (<= 128)", d);
+  if (init_from_data) {
+    count_launch();
+    strided_init_kernel<<<blocks_for(static_cast<int64_t>(k) * d, 256), 256, 0, s>>>(x, n, d, k, centers);
+    B2_CUDA(cudaGetLastError());
+  }
+  // data-side planes (the dataset plays the "query" role of the scan)
+  tc_rows_tmp xp;
+  xp.build(s, x, n, d, true);
+  dbuf<float> xn(static_cast<size_t>(n), s), cn(static_cast<size_t>(k), s), sums(static_cast<size_t>(k) * d, s),
+    counts(static_cast<size_t>(k), s), scores(static_cast<size_t>(n), s);
+  dbuf<uint32_t> labels(static_cast<size_t>(n), s);
+  dbuf<double> acc(1, s);
+  dbuf<int> n_reseeded(1, s);
+  row_norms(s, x, n, d, d, xn.data());
+  tc_rows cp;
+  double prev = -1.0;
+  int it      = 0;
+  for (; it < std::max(n_iters, 1); ++it) {
+    row_norms(s, centers, k, d, d, cn.data());
+    cp.build(s, centers, k, d, cn.data(), true);
+    assign_nearest(res, xp.hi.data(), xp.lo.data(), n, xp.rows_pad, xp.Kp, cp, labels.data(), scores.data());
+    if (n_iters == 0) break;  // assignment only
+    update_centers(s, x, n, d, labels.data(), nullptr, k, centers, sums.data(), counts.data());
+    if (balance && k > 1) {
+      B2_CUDA(cudaMemsetAsync(n_reseeded.data(), 0, sizeof(int), s));
+      count_launch();
+      reseed_small_kernel<<<blocks_for(k, 128), 128, 0, s>>>(x, n, d, labels.data(), counts.data(), k,
+                                                              static_cast<float>(n) / k, it, centers, n_reseeded.data());
+      B2_CUDA(cudaGetLastError());
+    }
+    if (tol > 0.0) {
+      B2_CUDA(cudaMemsetAsync(acc.data(), 0, sizeof(double), s));
+      count_launch();
+      sum_scores_kernel<<<256, 256, 0, s>>>(scores.data(), xn.data(), n, acc.data());
+      double cur = 0;
+      B2_CUDA(cudaMemcpyAsync(&cur, acc.data(), sizeof(double), cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaStreamSynchronize(s));
+      if (prev >= 0 && std::abs(prev - cur) <= tol * std::max(prev, 1e-30)) { prev = cur; ++it; break; }
+      prev = cur;
+    }
+  }
+  if (iters_done) *iters_done = it;
+  if (inertia) {
+    // inertia of the returned centres
+    row_norms(s, centers, k, d, d, cn.data());
+    cp.build(s, centers, k, d, cn.data(), true);
+    assign_nearest(res, xp.hi.data(), xp.lo.data(), n, xp.rows_pad, xp.Kp, cp, labels.data(), scores.data());
+    B2_CUDA(cudaMemsetAsync(acc.data(), 0, sizeof(double), s));
+    count_launch();
+    sum_scores_kernel<<<256, 256, 0, s>>>(scores.data(), xn.data(), n, acc.data());
+    B2_CUDA(cudaMemcpyAsync(inertia, acc.data(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+}  // namespace b200

@@ -26,41 +26,50 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace b200 {
 namespace {
 
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kQueue     = 40;         // per-thread pending-insert queue (flushed when > kQueue-32 before a 32-col chunk)
-constexpr int kThreads   = 192;
+constexpr int kChunk     = 16;         // accumulator columns per tcgen05.ld
+constexpr int kQueue     = 24;         // per-thread pending-insert queue; flushed (warp-convergently) when > kQueue - kChunk
 
-template <int KB, int NPL>
+template <int KB, int NPL, int EPIW>
 struct cfg {
+  static constexpr int threads     = 64 + 32 * EPIW;
   static constexpr int stages      = NPL == 2 ? 3 : 6;
   static constexpr int a_bytes     = NPL * KB * kTileBytes;
   static constexpr int stage_bytes = NPL * kTileBytes;
   static constexpr int n_bars      = 2 * stages + 2 + 4;
   static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + stages * stage_bytes + 2 * 128 * 4 /*hn*/ +
-                                 kQueue * 128 * 8 /*queues*/ + n_bars * 8 + 16;
+                                 kQueue * (32 * EPIW) * 8 /*queues*/ + n_bars * 8 + 16;
 };
 
-template <int KB, int NPL, int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+// KC > 0: fused top-KC epilogue.  KC == 0: "store" epilogue — every score of the tile is written to
+// out_score[out_off + row * out_row_stride + (column within the item's range)] (dense distance block).
+// EPIW = 4: one epilogue warp per TMEM lane quarter (128 columns each); EPIW = 8: two per quarter
+// (64 columns each, two candidate lists per query row and item).
+template <int KB, int NPL, int KC, int EPIW>
+__global__ void __launch_bounds__(64 + 32 * EPIW, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const float* __restrict__ hn, const tc_item* __restrict__ items, int n_items,
-               float* __restrict__ out_score, uint32_t* __restrict__ out_pos, int64_t out_row_stride)
+               const float* __restrict__ hn, const tc_item* __restrict__ items, int n_items_host,
+               const int* __restrict__ n_items_dev, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
+               int64_t out_row_stride, int dbg_skip_epilogue)
 {
-  using C = cfg<KB, NPL>;
+  using C = cfg<KB, NPL, EPIW>;
+  constexpr int kEpiThreads = 32 * EPIW;
+  const int n_items = n_items_dev ? *n_items_dev : n_items_host;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA   = base;
   uint8_t* sB   = sA + C::a_bytes;
   float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);
   float* qv     = sHn + 2 * 128;
-  uint32_t* qi  = reinterpret_cast<uint32_t*>(qv + kQueue * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qi + kQueue * 128);
+  uint32_t* qi  = reinterpret_cast<uint32_t*>(qv + kQueue * kEpiThreads);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qi + kQueue * kEpiThreads);
   uint64_t* full    = bars;
   uint64_t* empty   = bars + C::stages;
   uint64_t* a_full  = bars + 2 * C::stages;
@@ -88,7 +97,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     ptx::mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
-      ptx::mbar_init(&tempty[s], 128);
+      ptx::mbar_init(&tempty[s], kEpiThreads);
     }
     ptx::fence_barrier_init();
   }
@@ -170,78 +179,123 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, 1 row per thread)
+    // ------------------------------------------------------------------ epilogue (EPIW warps, 1 row x (512/EPIW) columns per thread)
     const int quarter = warp & 3;             // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int row     = quarter * 32 + lane;  // accumulator row == query row within the tile
+    const int half    = (warp - 2) >> 2;      // which column range of the tile (0 when EPIW == 4)
+    const int et      = half * 128 + row;     // slot in the queue arrays
+    constexpr int kCols   = 512 / EPIW;       // columns per thread and tile
+    constexpr int kChunks = kCols / kChunk;
+    const int col0        = half * kCols;
     uint32_t acc = 0, acc_phase = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const tc_item item = items[it];
-      float lv[KC];
-      uint32_t li[KC];
-#pragma unroll
-      for (int j = 0; j < KC; ++j) { lv[j] = INFINITY; li[j] = 0xffffffffu; }
-      float thr = INFINITY;
-      int cnt   = 0;
-
-      auto flush = [&]() {
-        for (int e = 0; e < cnt; ++e) {
-          const float s    = qv[e * 128 + row];
-          const uint32_t p = qi[e * 128 + row];
-          if (s < lv[KC - 1]) {
-#pragma unroll
-            for (int j = KC - 1; j > 0; --j) {
-              if (s < lv[j - 1]) { lv[j] = lv[j - 1]; li[j] = li[j - 1]; }
-              else if (s < lv[j]) { lv[j] = s; li[j] = p; }
-            }
-            if (s < lv[0]) { lv[0] = s; li[0] = p; }
-          }
-        }
-        cnt = 0;
-        thr = lv[KC - 1];
-      };
-
-      const float* hn_item = hn + item.b_row0;
-      float hn_reg         = item.n_tiles ? hn_item[row] : 0.f;
-      for (uint32_t t = 0; t < item.n_tiles; ++t) {
-        sHn[acc * 128 + row] = hn_reg;
-        ptx::named_bar_sync(1, 128);
-        if (t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
-        ptx::mbar_wait(&tfull[acc], acc_phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t pos0 = item.b_row0 + t * 128;
+    if constexpr (KC == 0) {
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const tc_item item   = items[it];
+        const float* hn_item = hn + item.b_row0;
+        float hn_reg         = (item.n_tiles && half == 0) ? hn_item[row] : 0.f;
+        float* orow          = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride;
+        const bool live      = static_cast<uint32_t>(row) < item.valid_rows;
+        for (uint32_t t = 0; t < item.n_tiles; ++t) {
+          if (half == 0) sHn[acc * 128 + row] = hn_reg;
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (half == 0 && t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
+          ptx::mbar_wait(&tfull[acc], acc_phase);
+          ptx::tc_fence_after_sync();
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          if (__any_sync(0xffffffffu, cnt > kQueue - 32)) flush();
-          __syncwarp();
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + ch * 32, v);
-          ptx::tmem_ld_wait();
-          const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + ch * 32);
+          for (int ch = 0; ch < kChunks; ++ch) {
+            uint32_t v[kChunk];
+            const int c0 = col0 + ch * kChunk;
+            ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + c0, v);
+            ptx::tmem_ld_wait();
+            if (live) {
+              const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + c0);
+              float4* o4       = reinterpret_cast<float4*>(orow + t * 128 + c0);
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 h = h4[c4];
-            const float s0 = h.x - __uint_as_float(v[c4 * 4 + 0]);
-            const float s1 = h.y - __uint_as_float(v[c4 * 4 + 1]);
-            const float s2 = h.z - __uint_as_float(v[c4 * 4 + 2]);
-            const float s3 = h.w - __uint_as_float(v[c4 * 4 + 3]);
-            const uint32_t p = pos0 + ch * 32 + c4 * 4;
-            if (s0 < thr) { qv[cnt * 128 + row] = s0; qi[cnt * 128 + row] = p + 0; ++cnt; }
-            if (s1 < thr) { qv[cnt * 128 + row] = s1; qi[cnt * 128 + row] = p + 1; ++cnt; }
-            if (s2 < thr) { qv[cnt * 128 + row] = s2; qi[cnt * 128 + row] = p + 2; ++cnt; }
-            if (s3 < thr) { qv[cnt * 128 + row] = s3; qi[cnt * 128 + row] = p + 3; ++cnt; }
+              for (int c4 = 0; c4 < kChunk / 4; ++c4) {
+                const float4 h = h4[c4];
+                o4[c4] = make_float4(h.x - __uint_as_float(v[c4 * 4 + 0]), h.y - __uint_as_float(v[c4 * 4 + 1]),
+                                     h.z - __uint_as_float(v[c4 * 4 + 2]), h.w - __uint_as_float(v[c4 * 4 + 3]));
+              }
+            }
           }
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tempty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&tempty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
-      flush();
-      if (static_cast<uint32_t>(row) < item.valid_rows) {
-        float* os    = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride;
-        uint32_t* op = out_pos + item.out_off + static_cast<int64_t>(row) * out_row_stride;
+    } else {
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const tc_item item = items[it];
+        float lv[KC > 0 ? KC : 1];
+        uint32_t li[KC > 0 ? KC : 1];
 #pragma unroll
-        for (int j = 0; j < KC; ++j) { os[j] = lv[j]; op[j] = li[j]; }
+        for (int j = 0; j < KC; ++j) { lv[j] = INFINITY; li[j] = 0xffffffffu; }
+        float thr = INFINITY;
+        int cnt   = 0;
+
+        auto flush = [&]() {
+          for (int e = 0; e < cnt; ++e) {
+            const float s    = qv[e * kEpiThreads + et];
+            const uint32_t p = qi[e * kEpiThreads + et];
+            if (s < lv[KC - 1]) {
+#pragma unroll
+              for (int j = KC - 1; j > 0; --j) {
+                if (s < lv[j - 1]) { lv[j] = lv[j - 1]; li[j] = li[j - 1]; }
+                else if (s < lv[j]) { lv[j] = s; li[j] = p; }
+              }
+              if (s < lv[0]) { lv[0] = s; li[0] = p; }
+            }
+          }
+          cnt = 0;
+          thr = lv[KC - 1];
+        };
+
+        const float* hn_item = hn + item.b_row0;
+        float hn_reg         = (item.n_tiles && half == 0) ? hn_item[row] : 0.f;
+        for (uint32_t t = 0; t < item.n_tiles; ++t) {
+          if (half == 0) sHn[acc * 128 + row] = hn_reg;
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (half == 0 && t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
+          ptx::mbar_wait(&tfull[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t pos0 = item.b_row0 + t * 128 + col0;
+          if (!dbg_skip_epilogue) {
+#pragma unroll 1
+            for (int ch = 0; ch < kChunks; ++ch) {
+              if (__any_sync(0xffffffffu, cnt > kQueue - kChunk)) flush();
+              __syncwarp();
+              uint32_t v[kChunk];
+              ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + col0 + ch * kChunk, v);
+              ptx::tmem_ld_wait();
+              const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + col0 + ch * kChunk);
+#pragma unroll
+              for (int c4 = 0; c4 < kChunk / 4; ++c4) {
+                const float4 h = h4[c4];
+                const float s0 = h.x - __uint_as_float(v[c4 * 4 + 0]);
+                const float s1 = h.y - __uint_as_float(v[c4 * 4 + 1]);
+                const float s2 = h.z - __uint_as_float(v[c4 * 4 + 2]);
+                const float s3 = h.w - __uint_as_float(v[c4 * 4 + 3]);
+                const uint32_t p = pos0 + ch * kChunk + c4 * 4;
+                if (s0 < thr) { qv[cnt * kEpiThreads + et] = s0; qi[cnt * kEpiThreads + et] = p + 0; ++cnt; }
+                if (s1 < thr) { qv[cnt * kEpiThreads + et] = s1; qi[cnt * kEpiThreads + et] = p + 1; ++cnt; }
+                if (s2 < thr) { qv[cnt * kEpiThreads + et] = s2; qi[cnt * kEpiThreads + et] = p + 2; ++cnt; }
+                if (s3 < thr) { qv[cnt * kEpiThreads + et] = s3; qi[cnt * kEpiThreads + et] = p + 3; ++cnt; }
+              }
+            }
+          }
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tempty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        flush();
+        if (static_cast<uint32_t>(row) < item.valid_rows) {
+          float* os    = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
+          uint32_t* op = out_pos + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
+#pragma unroll
+          for (int j = 0; j < KC; ++j) { os[j] = lv[j]; op[j] = li[j]; }
+        }
       }
     }
   }
@@ -285,22 +339,30 @@ CUtensorMap make_plane_map(const __nv_bfloat16* ptr, int64_t rows, int Kp)
   return m;
 }
 
-template <int KB, int NPL, int KC>
-void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-            const CUtensorMap& b_lo, const float* hn, const tc_item* items, int n_items, float* out_score,
-            uint32_t* out_pos, int64_t out_row_stride)
+int env_int(const char* name, int dflt)
 {
-  auto kern = tc_scan_kernel<KB, NPL, KC>;
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int KB, int NPL, int KC, int EPIW>
+void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+            const CUtensorMap& b_lo, const float* hn, const tc_item* items, int n_items, const int* n_items_dev,
+            float* out_score, uint32_t* out_pos, int64_t out_row_stride)
+{
+  auto kern = tc_scan_kernel<KB, NPL, KC, EPIW>;
+  using C   = cfg<KB, NPL, EPIW>;
+  static const int skip_epi = env_int("CUVS_B200_TC_SKIP_EPI", 0);  // profiling knob: MMA/TMA pipeline only
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg<KB, NPL>::smem)));
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
     attr_set = true;
   }
   int grid = n_items < sm_count ? n_items : sm_count;
   timed_section ts("tc_scan", stream);
   count_launch();
-  kern<<<grid, kThreads, cfg<KB, NPL>::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, out_score, out_pos,
-                                                        out_row_stride);
+  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, n_items_dev, out_score, out_pos,
+                                               out_row_stride, skip_epi);
   B2_CUDA(cudaGetLastError());
 }
 
@@ -338,6 +400,12 @@ __global__ void half_norms_kernel(const float* __restrict__ xn, int64_t n, int64
 
 }  // namespace
 
+int tc_lists_per_item()
+{
+  static const int epiw = env_int("CUVS_B200_TC_EPIW", 8);
+  return epiw == 4 ? 1 : 2;
+}
+
 bool tc_supported(int device, int d)
 {
   int major = 0;
@@ -366,24 +434,29 @@ void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows
 
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
-                  const float* hn, const tc_item* items_dev, int n_items, int KC, int passes, float* out_score,
-                  uint32_t* out_pos, int64_t out_row_stride)
+                  const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride)
 {
-  if (n_items == 0) return;
+  if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
   B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
-  B2_EXPECTS(KC == 16 || KC == 32, "tc_scan_topk: KC must be 16 or 32");
+  B2_EXPECTS(KC == 0 || KC == 16 || KC == 32, "tc_scan_topk: KC must be 0 (store), 16 or 32");
   B2_EXPECTS(passes == 1 || passes == 3, "tc_scan_topk: passes must be 1 or 3");
   B2_EXPECTS(passes == 1 || (a_lo && b_lo), "tc_scan_topk: lo planes required for 3-pass mode");
-  const int sms = sm_count_of(device);
+  const int sms  = sm_count_of(device);
+  const int epiw = tc_lists_per_item() * 4;
   CUtensorMap mA  = make_plane_map(a_hi, a_rows_pad, Kp);
   CUtensorMap mB  = make_plane_map(b_hi, b_rows_pad, Kp);
   CUtensorMap mAl = passes == 3 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
   CUtensorMap mBl = passes == 3 ? make_plane_map(b_lo, b_rows_pad, Kp) : mB;
 #define B2_TC_CASE(KB_, NPL_, KC_)                                                                                     \
   if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
-    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, out_score, out_pos, out_row_stride);
-  B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32)
-  B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32)
+  {                                                                                                                    \
+    if (epiw == 8)                                                                                                     \
+      return launch<KB_, NPL_, KC_, 8>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride); \
+    return launch<KB_, NPL_, KC_, 4>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride);   \
+  }
+  B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 2, 0)
+  B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 2, 0)
 #undef B2_TC_CASE
   B2_FAIL("tc_scan_topk: no kernel for Kp=%d passes=%d KC=%d", Kp, passes, KC);
 }

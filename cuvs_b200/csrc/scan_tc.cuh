@@ -16,7 +16,7 @@ constexpr int kTcTile = 128;  // rows of A (queries) and rows of B (dataset) per
 
 /** One unit of work: 128 query rows against a contiguous range of 128-row dataset tiles. */
 struct tc_item {
-  uint32_t a_row0;      // first row in the A planes (multiple of 128)
+  uint32_t a_row0;      // first row in the A planes (any row; 128 rows are read)
   uint32_t b_row0;      // first row in the B planes (multiple of 128)
   uint32_t n_tiles;     // number of 128-row B tiles to scan
   uint32_t valid_rows;  // rows of the A tile that are real queries (<= 128)
@@ -25,6 +25,10 @@ struct tc_item {
 
 inline int tc_pad_k(int d) { return (d + 63) / 64 * 64; }
 inline int64_t tc_pad_rows(int64_t n) { return (n + kTcTile - 1) / kTcTile * kTcTile; }
+
+/** Candidate lists the kernel emits per (item, query row): 1 or 2 (two epilogue warps per TMEM lane quarter,
+ *  each owning half of the tile's columns).  Every list holds KC entries; list j sits at +j*KC. */
+int tc_lists_per_item();
 
 /** True when the device/shape combination is served by the tcgen05 kernel (sm_100, Kp <= 128). */
 bool tc_supported(int device, int d);
@@ -40,14 +44,17 @@ void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld,
 void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn);
 
 /**
- * Run the scan.  For every item and every valid row r the kernel writes KC (score, position)
- * pairs, sorted best-first, at out_off + r * out_row_stride (+0..KC-1); empty slots hold
+ * Run the scan.  For every item and every valid row r the kernel writes tc_lists_per_item() lists of KC
+ * (score, position) pairs, each sorted best-first, at out_off + r * out_row_stride (+0..lists*KC-1); empty slots hold
  * (+inf, 0xffffffff).  `passes` = 3 uses hi*hi + lo*hi + hi*lo (fp32-grade products), 1 uses hi*hi.
- * KC must be 16 or 32.
+ * KC must be 16 or 32 — or 0 for the dense "store" epilogue: all scores of the item are written to
+ * out_score[out_off + r * out_row_stride + j], j = column offset inside the item's row range (out_pos unused).
+ * `n_items` is the host-known count or an upper bound; when `n_items_dev` is non-null the kernel reads the
+ * exact count from it (work lists built on the device, no host round trip).
  */
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
-                  const float* hn, const tc_item* items_dev, int n_items, int KC, int passes, float* out_score,
-                  uint32_t* out_pos, int64_t out_row_stride);
+                  const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride);
 
 }  // namespace b200
