@@ -272,7 +272,7 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
 static approx_map bf_approx_map(const bf_index& idx)
 {
   approx_map am;
-  am.eps_rel = 1.0f / 8192.0f;  // 2^-13: > 8x the split-bf16 + fp32-accumulation error bound
+  am.eps_rel = 1.0f / 32768.0f;  // 2^-15: ~3x the split-bf16 bound 3*2^-18*2|q||x| <= 2^-16.4 (|q|^2+|x|^2), ~9x the observed max
   if (idx.metric == InnerProduct) { am.sa = -1.f; am.eq = 1.f; am.ec = idx.xn_max; }
   else if (idx.metric == CosineExpanded) { am.sa = 1.f; am.sc = 1.f; am.eq = 0.f; am.ec = 2.f; }
   else { am.sa = 2.f; am.sb = 1.f; am.eq = 1.f; am.ec = idx.xn_max; }

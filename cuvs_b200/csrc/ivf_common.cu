@@ -45,12 +45,14 @@ __global__ void first_of_rows_kernel(const uint32_t* __restrict__ pos, const flo
 }
 
 // ---- probe bucketing -----------------------------------------------------------------------
-__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, uint32_t* __restrict__ counts)
+// probes of empty lists (e.g. lists owned by another shard) are dropped here
+__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, const int64_t* __restrict__ list_offsets,
+                                    uint32_t* __restrict__ counts)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
   uint32_t l = probes[t];
-  if (l != 0xffffffffu) atomicAdd(&counts[l], 1u);
+  if (l != 0xffffffffu && list_offsets[l + 1] > list_offsets[l]) atomicAdd(&counts[l], 1u);
 }
 
 // single CTA: exclusive scans over lists of (a) pair counts, (b) item counts ceil(cnt/128)
@@ -86,18 +88,18 @@ __global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __rest
     if (threadIdx.x == 1023) { run_pairs += s_pairs[1023]; run_items += s_items[1023]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_items = static_cast<int>(run_items);
+  if (threadIdx.x == 0) { n_items[0] = static_cast<int>(run_items); n_items[1] = static_cast<int>(run_pairs); }
 }
 
 __global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes,
-                                      const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cursor,
-                                      uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_query,
-                                      uint32_t* __restrict__ pair_list)
+                                      const int64_t* __restrict__ list_offsets, const uint32_t* __restrict__ pair_off,
+                                      uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_of,
+                                      uint32_t* __restrict__ pair_query, uint32_t* __restrict__ pair_list)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
   uint32_t l = probes[t];
-  if (l == 0xffffffffu) { slot_of[t] = 0xffffffffu; return; }
+  if (l == 0xffffffffu || list_offsets[l + 1] <= list_offsets[l]) { slot_of[t] = 0xffffffffu; return; }
   uint32_t slot    = pair_off[l] + atomicAdd(&cursor[l], 1u);
   slot_of[t]       = slot;
   pair_query[slot] = static_cast<uint32_t>(t / n_probes);
@@ -126,15 +128,15 @@ __global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, cons
   }
 }
 
-__global__ void gather_rows_kernel(const uint4* __restrict__ src, const uint32_t* __restrict__ pair_query, int64_t n_pairs,
-                                   int64_t rows_total, int vec_per_row, uint4* __restrict__ dst)
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const uint32_t* __restrict__ pair_query,
+                                   const int* __restrict__ n_live, int64_t rows_total, int vec_per_row, uint4* __restrict__ dst)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= rows_total * vec_per_row) return;
   int64_t r = t / vec_per_row;
   int v     = static_cast<int>(t % vec_per_row);
   uint4 val = make_uint4(0, 0, 0, 0);
-  if (r < n_pairs) val = src[static_cast<int64_t>(pair_query[r]) * vec_per_row + v];
+  if (r < *n_live) val = src[static_cast<int64_t>(pair_query[r]) * vec_per_row + v];
   dst[t] = val;
 }
 
@@ -322,26 +324,26 @@ void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_pro
   out.pair_query.alloc(static_cast<size_t>(total), s);
   out.pair_list.alloc(static_cast<size_t>(total), s);
   out.items.alloc(static_cast<size_t>(out.max_items), s);
-  out.n_items.alloc(1, s);
+  out.n_items.alloc(2, s);
   dbuf<uint32_t> counts(static_cast<size_t>(n_lists), s), pair_off(static_cast<size_t>(n_lists), s),
     item_off(static_cast<size_t>(n_lists), s), cursor(static_cast<size_t>(n_lists), s);
   B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * n_lists, s));
   count_launch(4);
-  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, counts.data());
+  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, list_offsets_dev, counts.data());
   scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), item_off.data(), out.n_items.data(), cursor.data());
-  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, pair_off.data(), cursor.data(),
+  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, list_offsets_dev, pair_off.data(), cursor.data(),
                                                                 out.slot_of.data(), out.pair_query.data(), out.pair_list.data());
   make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), item_off.data(),
                                                                    list_offsets_dev, n_lists, KC, out.items.data());
   B2_CUDA(cudaGetLastError());
 }
 
-void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, int64_t n_pairs, int64_t rows_total,
+void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, const int* n_live, int64_t rows_total,
                       int Kp, __nv_bfloat16* dst)
 {
   const int vec = Kp * 2 / 16;
   count_launch();
-  gather_rows_kernel<<<blocks_for(rows_total * vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(src), pair_query, n_pairs,
+  gather_rows_kernel<<<blocks_for(rows_total * vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(src), pair_query, n_live,
                                                                         rows_total, vec, reinterpret_cast<uint4*>(dst));
   B2_CUDA(cudaGetLastError());
 }

@@ -58,7 +58,7 @@ void assign_nearest(resources* res, const __nv_bfloat16* x_hi, const __nv_bfloat
 struct probe_buckets {
   dbuf<uint32_t> slot_of, pair_query, pair_list;
   dbuf<tc_item> items;
-  dbuf<int> n_items;   // device scalar
+  dbuf<int> n_items;   // device: [0] = number of work items, [1] = number of live pairs (slots in use)
   int max_items = 0;   // host upper bound
   int64_t n_pairs = 0;
 };
@@ -66,8 +66,8 @@ void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_pro
                    const int64_t* list_offsets_dev /*[n_lists+1], padded row offsets (multiples of 128)*/, int KC,
                    probe_buckets& out);
 
-/** Gather bf16 rows: dst[slot] = src[pair_query[slot]] (Kp elements each); rows >= n_pairs are zeroed up to rows_total. */
-void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, int64_t n_pairs, int64_t rows_total,
+/** Gather bf16 rows: dst[slot] = src[pair_query[slot]] (Kp elements each); rows >= *n_live are zeroed up to rows_total. */
+void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, const int* n_live, int64_t rows_total,
                       int Kp, __nv_bfloat16* dst);
 
 /** Per query, concatenate the KC candidates of each of its probes: out [nq, n_probes*KC]. */

@@ -62,9 +62,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   using C = cfg<KB, NPL, EPIW>;
   constexpr int kEpiThreads = 32 * EPIW;
   const int n_items = n_items_dev ? *n_items_dev : n_items_host;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA   = base;
+  // 1024-byte alignment is what SWIZZLE_128B operand tiles need; declared on the array (no integer
+  // round-trip of the pointer) so that the compiler keeps every access in the shared address space.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* sA   = smem_raw;
   uint8_t* sB   = sA + C::a_bytes;
   float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);
   float* qv     = sHn + 2 * 128;
@@ -261,26 +263,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ptx::tc_fence_after_sync();
           const uint32_t pos0 = item.b_row0 + t * 128 + col0;
           if (!dbg_skip_epilogue) {
+            // 32 accumulator columns per tcgen05.ld, examined as two groups of 16.  Hot path per group:
+            // 16 FADD (s = hn - acc) + a 15-op min tree + ONE compare/branch; the per-element test only
+            // runs when the group's minimum beats the thread's current k'-th best.
 #pragma unroll 1
-            for (int ch = 0; ch < kChunks; ++ch) {
-              if (__any_sync(0xffffffffu, cnt > kQueue - kChunk)) flush();
-              __syncwarp();
-              uint32_t v[kChunk];
-              ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + col0 + ch * kChunk, v);
+            for (int ch = 0; ch < kCols / 32; ++ch) {
+              uint32_t v[32];
+              ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + col0 + ch * 32, v);
               ptx::tmem_ld_wait();
-              const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + col0 + ch * kChunk);
 #pragma unroll
-              for (int c4 = 0; c4 < kChunk / 4; ++c4) {
-                const float4 h = h4[c4];
-                const float s0 = h.x - __uint_as_float(v[c4 * 4 + 0]);
-                const float s1 = h.y - __uint_as_float(v[c4 * 4 + 1]);
-                const float s2 = h.z - __uint_as_float(v[c4 * 4 + 2]);
-                const float s3 = h.w - __uint_as_float(v[c4 * 4 + 3]);
-                const uint32_t p = pos0 + ch * kChunk + c4 * 4;
-                if (s0 < thr) { qv[cnt * kEpiThreads + et] = s0; qi[cnt * kEpiThreads + et] = p + 0; ++cnt; }
-                if (s1 < thr) { qv[cnt * kEpiThreads + et] = s1; qi[cnt * kEpiThreads + et] = p + 1; ++cnt; }
-                if (s2 < thr) { qv[cnt * kEpiThreads + et] = s2; qi[cnt * kEpiThreads + et] = p + 2; ++cnt; }
-                if (s3 < thr) { qv[cnt * kEpiThreads + et] = s3; qi[cnt * kEpiThreads + et] = p + 3; ++cnt; }
+              for (int g = 0; g < 2; ++g) {
+                if (__any_sync(0xffffffffu, cnt > kQueue - kChunk)) flush();
+                const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + col0 + ch * 32 + g * 16);
+                float sc[16];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  const float4 h = h4[c4];
+                  sc[c4 * 4 + 0] = h.x - __uint_as_float(v[g * 16 + c4 * 4 + 0]);
+                  sc[c4 * 4 + 1] = h.y - __uint_as_float(v[g * 16 + c4 * 4 + 1]);
+                  sc[c4 * 4 + 2] = h.z - __uint_as_float(v[g * 16 + c4 * 4 + 2]);
+                  sc[c4 * 4 + 3] = h.w - __uint_as_float(v[g * 16 + c4 * 4 + 3]);
+                }
+                float m01 = fminf(sc[0], sc[1]), m23 = fminf(sc[2], sc[3]), m45 = fminf(sc[4], sc[5]), m67 = fminf(sc[6], sc[7]);
+                float m89 = fminf(sc[8], sc[9]), mab = fminf(sc[10], sc[11]), mcd = fminf(sc[12], sc[13]), mef = fminf(sc[14], sc[15]);
+                const float mn = fminf(fminf(fminf(m01, m23), fminf(m45, m67)), fminf(fminf(m89, mab), fminf(mcd, mef)));
+                if (mn < thr) {
+                  const uint32_t p = pos0 + ch * 32 + g * 16;
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    if (sc[c] < thr) { qv[cnt * kEpiThreads + et] = sc[c]; qi[cnt * kEpiThreads + et] = p + c; ++cnt; }
+                  }
+                }
               }
             }
           }

@@ -48,7 +48,7 @@ CUVS_EXPORT cuvsError_t cuvsIvfFlatIndexDestroy(cuvsIvfFlatIndex_t index);
 
 CUVS_EXPORT cuvsError_t cuvsIvfFlatIndexGetNLists(cuvsIvfFlatIndex_t index, int64_t* n_lists);
 CUVS_EXPORT cuvsError_t cuvsIvfFlatIndexGetDim(cuvsIvfFlatIndex_t index, int64_t* dim);
-/* centers: caller-allocated [n_lists, dim] f32 device tensor that receives a copy. */
+/* centers: filled as a non-owning [n_lists, dim] f32 device view (shape owned by the tensor, freed by its deleter). */
 CUVS_EXPORT cuvsError_t cuvsIvfFlatIndexGetCenters(cuvsIvfFlatIndex_t index,
                                                    DLManagedTensor* centers);
 

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuvs/core/c_api.h>
 #include <cuvs/neighbors/brute_force.h>
+#include <cuvs/neighbors/ivf_flat.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -31,6 +32,12 @@ CUVS_EXPORT cuvsError_t cuvsB200BruteForceCandidates(cuvsResources_t res,
                                                      DLManagedTensor* queries,
                                                      DLManagedTensor* cand_pos,
                                                      DLManagedTensor* cand_score);
+/* IVF-Flat list introspection (the reference exposes the equivalent only for IVF-PQ:
+ * cuvsIvfPqIndexGetListSizes / cuvsIvfPqIndexGetListIndices).  Non-owning views into the index. */
+CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetListSizes(cuvsIvfFlatIndex_t index, DLManagedTensor* list_sizes /*[n_lists] u32*/);
+CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetListIndices(cuvsIvfFlatIndex_t index, uint32_t label, DLManagedTensor* ids /*[size] i64*/);
+CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t* size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,150 @@
+"""GPU parity: cuvsIvfPq{Build,BuildPrecomputed,Search,Extend,Transform,Serialize} via the C ABI vs the oracle.
+
+Element-wise: the library's own quantizers (centres, rotation, codebooks), list membership and codes are
+read back through the reference's getter API and fed to the oracle's LUT-sum search
+(oracle_ivf_pq_search); the LUT-scan kernel must reproduce it (fp32 LUT: same ids except at ties,
+distances to 1e-5), the decoded-tile tensor-core path within PQ-noise-free tolerance 2e-3.
+Recall floors follow cpp/tests/neighbors/ann_ivf_pq.cuh:978-1064 (>= 0.86 at pq_bits 8, defaults
+4096 x 64, 1024 queries, k 32, n_lists 32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.util import clustered, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _mod():
+    from cuvs_b200.neighbors import ivf_pq
+    return ivf_pq
+
+
+def _unpack(index):
+    """-> (offsets, codes [n, pq_dim] one code per byte, ids) from the C getters (8-bit codes here)."""
+    sizes = index.list_sizes.cpu().numpy().astype(np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    codes, ids = [], []
+    for l in range(index.n_lists):
+        if sizes[l]:
+            codes.append(index.list_data(l).cpu().numpy())
+            ids.append(index.list_indices(l).cpu().numpy())
+    return offs, np.concatenate(codes), np.concatenate(ids)
+
+
+def _oracle(index, qs, n_probes, k, metric, lut="f32", dist="f32"):
+    offs, codes, ids = _unpack(index)
+    return oracle.ivf_pq_search(index.centers.cpu().numpy(), index.centers_rot.cpu().numpy(), index.rotation_matrix.cpu().numpy(),
+                                index.pq_centers.cpu().numpy(), offs, codes, ids, qs, n_probes, k, metric, pq_bits=8,
+                                lut_dtype=lut, dist_dtype=dist)
+
+
+def _search(index, qs, n_probes, k, path, **kw):
+    m = _mod()
+    os.environ["CUVS_B200_PQ_PATH"] = path
+    d, i = m.search(m.SearchParams(n_probes=n_probes, **kw), index, torch.from_numpy(qs).cuda(), k)
+    return d.cpu().numpy(), i.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def small_index():
+    m = _mod()
+    ds = uniform(4096, 64, 1234, 0.1, 2.0)  # ann_ivf_pq.cuh:150-168 distribution
+    qs = uniform(1024, 64, 4321, 0.1, 2.0)
+    index = m.build(m.IndexParams(n_lists=32, pq_dim=32, pq_bits=8, kmeans_n_iters=20), torch.from_numpy(ds).cuda())
+    return ds, qs, index
+
+
+def test_index_shapes_and_packing(small_index):
+    ds, qs, index = small_index
+    assert (index.n_lists, index.dim, index.pq_dim, index.pq_len, index.pq_bits, len(index)) == (32, 64, 32, 2, 8, 4096)
+    assert tuple(index.pq_centers.shape) == (32, 2, 256) and tuple(index.centers_padded.shape) == (32, 72)
+    cp = index.centers_padded.cpu().numpy()
+    np.testing.assert_allclose(cp[:, 64], (cp[:, :64] ** 2).sum(1), rtol=1e-5)  # |c|^2 column (ivf_pq_index.cu:78-80)
+    offs, codes, ids = _unpack(index)
+    assert sorted(ids.tolist()) == list(range(4096)) and codes.shape == (4096, 32)
+    # codes really are the nearest codebook entries of the rotated residuals (transform == what is stored)
+    m = _mod()
+    labels, tcodes = m.transform(index, torch.from_numpy(ds[:512]).cuda())
+    pos = {int(i): j for j, i in enumerate(ids)}
+    stored = codes[[pos[i] for i in range(512)]]
+    assert (tcodes.cpu().numpy() == stored).all()
+
+
+@pytest.mark.parametrize("lut,dist,tol", [("f32", "f32", 1e-5), ("f16", "f32", 1e-5), ("fp8", "f32", 1e-5), ("f16", "f16", 2e-2)])
+def test_lut_scan_matches_oracle(small_index, lut, dist, tol):
+    ds, qs, index = small_index
+    kw = {"lut_dtype": {"f32": np.float32, "f16": np.float16, "fp8": np.uint8}[lut],
+          "internal_distance_dtype": {"f32": np.float32, "f16": np.float16}[dist]}
+    d, i = _search(index, qs, 8, 32, "lut", **kw)
+    rd, ri = _oracle(index, qs, 8, 32, "sqeuclidean", lut, dist)
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=max(tol, 1e-5)) >= 0.999
+    if dist == "f32":
+        same = i == ri
+        assert same.mean() >= 0.99
+        np.testing.assert_allclose(d[same], rd[same], rtol=tol, atol=tol)
+
+
+def test_tensor_core_path_matches_lut_semantics(small_index):
+    ds, qs, index = small_index
+    d, i = _search(index, qs, 8, 32, "tc")
+    rd, ri = _oracle(index, qs, 8, 32, "sqeuclidean")
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=2e-3) >= 0.995
+    same = i == ri
+    assert same.mean() >= 0.97
+    np.testing.assert_allclose(d[same], rd[same], rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("path", ["lut", "tc"])
+def test_reference_recall_floor(small_index, path):
+    ds, qs, index = small_index
+    d, i = _search(index, qs, 20, 32, path)
+    gd, gi = oracle.knn(ds, qs, 32)
+    assert oracle.recall(i, gi) >= 0.86  # ann_ivf_pq.cuh:978-1064 (pq_bits=8)
+
+
+@pytest.mark.parametrize("metric,path", [("inner_product", "lut"), ("inner_product", "tc"), ("euclidean", "tc")])
+def test_other_metrics(metric, path):
+    m = _mod()
+    ds, centers = clustered(20000, 96, 3, n_centers=64)
+    qs, _ = clustered(200, 96, 4, centers=centers)
+    index = m.build(m.IndexParams(n_lists=64, pq_dim=48, metric=metric, kmeans_n_iters=10), torch.from_numpy(ds).cuda())
+    d, i = _search(index, qs, 16, 10, path)
+    rd, ri = _oracle(index, qs, 16, 10, metric)
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=3e-3) >= 0.99
+
+
+def test_build_precomputed_extend_save_load(tmp_path, small_index):
+    m = _mod()
+    ds, qs, index = small_index
+    params = m.IndexParams(n_lists=32, pq_dim=32, pq_bits=8)
+    pre = m.build_precomputed(params, 64, index.pq_centers, index.centers, index.centers_rot, index.rotation_matrix)
+    assert len(pre) == 0
+    ids = np.arange(4096, dtype=np.int64) + 100
+    m.extend(pre, torch.from_numpy(ds[:2000]).cuda(), torch.from_numpy(ids[:2000]).cuda())
+    m.extend(pre, torch.from_numpy(ds[2000:]).cuda(), torch.from_numpy(ids[2000:]).cuda())
+    assert len(pre) == 4096
+    d1, i1 = _search(pre, qs[:100], 8, 10, "lut")
+    d0, i0 = _search(index, qs[:100], 8, 10, "lut")
+    assert ((i1 - 100) == i0).mean() >= 0.999  # same quantizers, same codes -> same answers
+    m.save(str(tmp_path / "pq.idx"), pre)
+    again = m.load(str(tmp_path / "pq.idx"))
+    d2, i2 = _search(again, qs[:100], 8, 10, "lut")
+    assert (i1 == i2).all() and (d1 == d2).all()
+
+
+def test_refine_restores_exact_order(small_index):
+    from cuvs_b200.neighbors import refine
+    ds, qs, index = small_index
+    d, i = _search(index, qs, 32, 32, "tc")
+    rd, ri = refine(torch.from_numpy(ds).cuda(), torch.from_numpy(qs).cuda(), torch.from_numpy(i).cuda(), k=10)
+    rd, ri = rd.cpu().numpy(), ri.cpu().numpy()
+    # refined distances are the exact fp32 distances of the returned ids, sorted
+    exact = ((qs[:, None, :] - ds[ri]) ** 2).sum(-1)
+    np.testing.assert_allclose(rd, exact, rtol=1e-5, atol=1e-5)
+    assert (np.diff(rd, axis=1) >= 0).all()
+    gd, gi = oracle.knn(ds, qs, 10)
+    assert oracle.recall(ri, gi) >= 0.95
