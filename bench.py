@@ -166,7 +166,121 @@ class BruteForceWorkload:
         return bool(ok)
 
 
-WORKLOADS = {"brute_force": BruteForceWorkload}
+class IvfPqWorkload:
+    """configs[2]: ivf_pq::search 10M x 128 f32, nlist=1024 pq_dim=64 nprobe=64, batch 10k (+ exact refine to reach recall)."""
+    dtype = "bf16 tensor-core scan of decoded PQ rows, fp32 accumulate; fp32 exact refine"
+    timing_section = "pq_scan"
+
+    def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=1024, pq_dim=64, n_probes=64, refine_ratio=4, seed=1234):
+        from cuvs_b200.neighbors import brute_force, ivf_pq, refine
+        self.n, self.d, self.nq, self.k = n, d, nq, k
+        self.n_lists, self.pq_dim, self.n_probes, self.refine_ratio = n_lists, pq_dim, n_probes, refine_ratio
+        self.name = (f"ivf_pq {n // 1_000_000}M x {d} f32, n_lists={n_lists} pq_dim={pq_dim} pq_bits=8 n_probes={n_probes}, "
+                     f"batch {nq}, k={k}, refine_ratio={refine_ratio}")
+        self.pq, self.refine = ivf_pq, refine
+        g = torch.Generator(device="cuda")
+        g.manual_seed(99)
+        centers = torch.randn((max(1, n // 1000), d), generator=g, device="cuda")
+        self.dataset = gen_clustered(n, d, seed, centers)
+        self.queries = gen_clustered(nq, d, seed + 3087, centers)
+        t0 = time.time()
+        self.index = ivf_pq.build(ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10), self.dataset)
+        torch.cuda.synchronize()
+        self.build_s = time.time() - t0
+        self.sp = ivf_pq.SearchParams(n_probes=n_probes)
+        self.kc = k * refine_ratio
+        self.cand = torch.empty((nq, self.kc), dtype=torch.int64, device="cuda")
+        self.cand_d = torch.empty((nq, self.kc), dtype=torch.float32, device="cuda")
+        self.h_queries = self.queries.cpu().pin_memory()
+        self.neighbors = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        # ground truth (exact, our brute force) for recall
+        bf = brute_force.build(self.dataset)
+        _, self.gt = brute_force.search(bf, self.queries, k)
+        del bf
+        self.recall = None
+
+    def _search(self, q, res):
+        if self.refine_ratio > 1:
+            self.pq.search(self.sp, self.index, q, self.kc, neighbors=self.cand, distances=self.cand_d, resources=res)
+            self.refine(self.dataset, q, self.cand, indices=self.neighbors, distances=self.distances, resources=res)
+        else:
+            self.pq.search(self.sp, self.index, q, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+
+    def step(self, res):
+        self._search(self.queries, res)
+
+    def e2e_step(self, res):
+        q = self.h_queries.to("cuda", non_blocking=True)
+        self._search(q, res)
+        self.h_neighbors.copy_(self.neighbors, non_blocking=True)
+        self.h_distances.copy_(self.distances, non_blocking=True)
+
+    def e2e_bytes(self):
+        return self.nq * self.d * 4, self.nq * self.k * 12
+
+    def units(self):
+        return self.nq
+
+    def check(self):
+        hit = (self.neighbors.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
+        self.recall = hit
+        return hit >= 0.95
+
+    def config(self):
+        sizes = self.index.list_sizes.float()
+        return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
+                "n_lists": self.n_lists, "pq_dim": self.pq_dim, "pq_bits": 8, "n_probes": self.n_probes,
+                "refine_ratio": self.refine_ratio, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "list_size_max_over_mean": round((sizes.max() / sizes.mean()).item(), 2),
+                "data": "clustered gaussians (SURVEY 8d), seed 1234/4321", "l2_flush": "256 MiB write between timed steps",
+                "parallelism": "single GPU"}
+
+    def scanned_rows(self):
+        """sum over (query, probe) pairs of the probed list's length (algorithmic scan volume)."""
+        c = self.index.centers
+        sizes = self.index.list_sizes.to(torch.int64)
+        tot = 0
+        for s in range(0, self.nq, 2048):
+            q = self.queries[s:s + 2048]
+            dist = (c * c).sum(1)[None, :] - 2.0 * q @ c.t()
+            pr = dist.topk(self.n_probes, dim=1, largest=False).indices
+            tot += int(sizes[pr].sum().item())
+        return tot
+
+    def roofline(self, kernel_ms, pk):
+        rows = self.scanned_rows()
+        flops = 2.0 * rows * self.d  # one multiply-add per (pair, row, component)
+        code_bytes = rows * self.pq_dim  # bytes of PQ codes the reference formulation streams (one read per pair)
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "tc_scan_kernel over decoded PQ rows (tcgen05 bf16, fused top-k')", "achieved": ach,
+                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "traffic": None, "kernel_ms": kernel_ms,
+                "scanned_rows": rows,
+                "reference_formulation": {"algorithmic_code_bytes": code_bytes,
+                                          "equivalent_GBps": code_bytes / (kernel_ms * 1e-3) / 1e9,
+                                          "frac_of_hbm_peak": code_bytes / (kernel_ms * 1e-3) / 1e9 / pk["hbm"]}}
+
+    def cpu_baseline(self, budget_s=20.0):
+        import oracle
+        ds = self.dataset[:1_000_000].cpu().numpy()
+        qs = self.queries[:64].cpu().numpy()
+        t0 = time.time()
+        oracle.knn(ds, qs[:8], self.k)
+        per_q = (time.time() - t0) / 8 * (self.n / 1_000_000)
+        m = int(max(4, min(64, budget_s / max(per_q, 1e-6))))
+        full = self.dataset.cpu().numpy()
+        t0 = time.time()
+        oracle.knn(full, qs[:m], self.k)
+        dt = time.time() - t0
+        return {"value": m / dt, "unit": "queries/s", "cores": oracle.num_threads(), "kind": "port",
+                "sample": f"{m} of {self.nq} queries, exact fp32 kNN over all {self.n} rows (oracle/oracle.c, OpenMP) — the "
+                          "reference has no CPU IVF-PQ search"}
+
+
+WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload}
 
 
 def launches():
@@ -188,7 +302,16 @@ def run_ours(args):
     from cuvs_b200.common import Resources
     lib.cuvsB200TimingTotalMs.restype = C.c_double
 
-    wl = WORKLOADS[args.workload](**({"n": args.n} if args.n else {}), **({"nq": args.nq} if args.nq else {}))
+    kw = {}
+    if args.n:
+        kw["n"] = args.n
+    if args.nq:
+        kw["nq"] = args.nq
+    if args.workload == "ivf_pq":
+        for name in ("n_lists", "n_probes", "refine_ratio", "pq_dim"):
+            if getattr(args, name):
+                kw[name] = getattr(args, name)
+    wl = WORKLOADS[args.workload](**kw)
     res = Resources()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -306,6 +429,10 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--n-lists", dest="n_lists", type=int, default=0)
+    ap.add_argument("--n-probes", dest="n_probes", type=int, default=0)
+    ap.add_argument("--refine-ratio", dest="refine_ratio", type=int, default=0)
+    ap.add_argument("--pq-dim", dest="pq_dim", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -284,15 +284,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                   sc[c4 * 4 + 2] = h.z - __uint_as_float(v[g * 16 + c4 * 4 + 2]);
                   sc[c4 * 4 + 3] = h.w - __uint_as_float(v[g * 16 + c4 * 4 + 3]);
                 }
-                float m01 = fminf(sc[0], sc[1]), m23 = fminf(sc[2], sc[3]), m45 = fminf(sc[4], sc[5]), m67 = fminf(sc[6], sc[7]);
-                float m89 = fminf(sc[8], sc[9]), mab = fminf(sc[10], sc[11]), mcd = fminf(sc[12], sc[13]), mef = fminf(sc[14], sc[15]);
-                const float mn = fminf(fminf(fminf(m01, m23), fminf(m45, m67)), fminf(fminf(m89, mab), fminf(mcd, mef)));
+                // quad minima -> group minimum; a row rarely has more than one quad with a hit
+                const float q0 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
+                const float q1 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
+                const float q2 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
+                const float q3 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
+                const float mn = fminf(fminf(q0, q1), fminf(q2, q3));
                 if (mn < thr) {
                   const uint32_t p = pos0 + ch * 32 + g * 16;
-#pragma unroll
-                  for (int c = 0; c < 16; ++c) {
-                    if (sc[c] < thr) { qv[cnt * kEpiThreads + et] = sc[c]; qi[cnt * kEpiThreads + et] = p + c; ++cnt; }
+#define B2_SCAN_QUAD(QM, BASE)                                                                                         \
+                  if (QM < thr) {                                                                                      \
+                    _Pragma("unroll") for (int c = BASE; c < BASE + 4; ++c) {                                          \
+                      if (sc[c] < thr) { qv[cnt * kEpiThreads + et] = sc[c]; qi[cnt * kEpiThreads + et] = p + c; ++cnt; } \
+                    }                                                                                                  \
                   }
+                  B2_SCAN_QUAD(q0, 0) B2_SCAN_QUAD(q1, 4) B2_SCAN_QUAD(q2, 8) B2_SCAN_QUAD(q3, 12)
+#undef B2_SCAN_QUAD
                 }
               }
             }
