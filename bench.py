@@ -94,6 +94,22 @@ def gen_clustered(n, d, seed, centers, sigma=0.25, device="cuda", chunk=1 << 20)
     return out
 
 
+def gen_manifold(n, d, seed, rank=16, noise=0.05, device="cuda", chunk=1 << 20):
+    """Embedding-like data: x = z A + noise * N(0, I_d), z ~ N(0, I_rank), A fixed (seed 99) — intrinsic dimension `rank`,
+    so nearest neighbours are meaningful (SIFT/DEEP-like), unlike iid or well-separated-cluster data in >= 96 dimensions."""
+    ga = torch.Generator(device=device)
+    ga.manual_seed(99)
+    A = torch.randn((rank, d), generator=ga, device=device) / rank ** 0.5
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        z = torch.randn((e - s, rank), generator=g, device=device)
+        out[s:e] = z @ A + noise * torch.randn((e - s, d), generator=g, device=device)
+    return out
+
+
 class BruteForceWorkload:
     """configs[1]: brute_force::search 1M x 128 f32 L2, batch 10k, k=10."""
     name = "brute_force 1M x 128 f32 L2 (sqeuclidean), batch 10k, k=10"
@@ -178,11 +194,8 @@ class IvfPqWorkload:
         self.name = (f"ivf_pq {n // 1_000_000}M x {d} f32, n_lists={n_lists} pq_dim={pq_dim} pq_bits=8 n_probes={n_probes}, "
                      f"batch {nq}, k={k}, refine_ratio={refine_ratio}")
         self.pq, self.refine = ivf_pq, refine
-        g = torch.Generator(device="cuda")
-        g.manual_seed(99)
-        centers = torch.randn((max(1, n // 1000), d), generator=g, device="cuda")
-        self.dataset = gen_clustered(n, d, seed, centers)
-        self.queries = gen_clustered(nq, d, seed + 3087, centers)
+        self.dataset = gen_manifold(n, d, seed)
+        self.queries = gen_manifold(nq, d, seed + 3087)
         t0 = time.time()
         self.index = ivf_pq.build(ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10), self.dataset)
         torch.cuda.synchronize()
@@ -235,8 +248,8 @@ class IvfPqWorkload:
                 "n_lists": self.n_lists, "pq_dim": self.pq_dim, "pq_bits": 8, "n_probes": self.n_probes,
                 "refine_ratio": self.refine_ratio, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
                 "list_size_max_over_mean": round((sizes.max() / sizes.mean()).item(), 2),
-                "data": "clustered gaussians (SURVEY 8d), seed 1234/4321", "l2_flush": "256 MiB write between timed steps",
-                "parallelism": "single GPU"}
+                "data": "rank-16 gaussian manifold in 128-d + 0.05 noise (embedding-like), seeds 1234/4321",
+                "l2_flush": "256 MiB write between timed steps", "parallelism": "single GPU"}
 
     def scanned_rows(self):
         """sum over (query, probe) pairs of the probed list's length (algorithmic scan volume)."""

@@ -1,0 +1,852 @@
+// CAGRA: graph-walk search kernel, index from (graph, dataset), simple graph build, C boundary.
+//
+// Reference path being replaced:
+//   index                 cpp/include/cuvs/neighbors/cagra.hpp:398-890
+//   plan / parameters     cpp/src/neighbors/detail/cagra/search_plan.cuh:99-428
+//   single-CTA kernel     cpp/src/neighbors/detail/cagra/jit_lto_kernels/search_single_cta_jit.cuh:55-451
+//   seeds / children      .../device_common_jit.cuh:36-179     hash   .../hashmap.hpp:23-145
+//   parent pickup / sort  .../search_single_cta_device_helpers.cuh:97-137, 277-623
+//   C wrapper             c/src/neighbors/cagra.cpp
+//
+// B200 formulation.  The walk is a chain of ~70 dependent iterations per query, each a
+// 256-byte adjacency read, ~64 random 384-byte vector gathers, a dedup against a small hash and a
+// 128-way sort: it is bound by memory LATENCY, so throughput comes from the number of independent
+// walks in flight, not from one walk's bandwidth.  The reference spends a whole CTA (>= 64 threads,
+// ~6 __syncthreads per iteration) per query; here ONE WARP owns a query end to end:
+//   * the internal top-k list and the candidate list live in registers (4 x 64-bit keys per lane),
+//     sorted by a shuffle-only bitonic network — no shared-memory round trips, no block barriers;
+//   * the visited set is the reference's small open-addressing hash, per warp in shared memory;
+//   * distances use teams of 8 lanes with 128-bit loads (384 B row = 3 x 16 B per lane), several
+//     candidates' loads issued back to back for memory-level parallelism;
+//   * 16 warps per CTA and ~2.5 KB of shared memory per warp keep 48-64 walks resident per SM
+//     (~8-9k concurrent walks per GPU), which is what hides the DRAM latency.
+// Semantics (seeds, hash, parent selection, termination) follow the reference exactly and are
+// restated on the CPU in oracle/oracle.c::oracle_cagra_search.
+#include "common.hpp"
+#include "exact.cuh"
+#include "select_k.cuh"
+#include "timing.hpp"
+
+#include <cuvs/neighbors/brute_force.h>
+#include <cuvs/neighbors/cagra.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <vector>
+
+namespace b200 {
+
+struct cagra_index {
+  int device              = 0;
+  cuvsDistanceType metric = L2Expanded;
+  int64_t n               = 0;
+  int dim                 = 0;
+  int ld                  = 0;  // row pitch in floats (rows padded to 16 bytes, cagra.hpp:610)
+  int degree              = 0;
+  const float* data       = nullptr;
+  const uint32_t* graph   = nullptr;
+  owned<float> data_own;
+  owned<uint32_t> graph_own;
+};
+
+namespace {
+
+inline unsigned blocks_for(int64_t n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+constexpr uint32_t kInvalid = 0xffffffffu;
+constexpr uint32_t kMsb     = 0x80000000u;
+
+__host__ __device__ __forceinline__ uint64_t xorshift64(uint64_t u)
+{
+  u ^= u >> 12;
+  u ^= u << 25;
+  u ^= u >> 27;
+  return u * 0x2545F4914F6CDD1DULL;
+}
+
+// hashmap.hpp:37-73 — open addressing, double hashing; returns 1 when newly inserted
+__device__ __forceinline__ uint32_t hash_insert(uint32_t* table, uint32_t bitlen, uint32_t key)
+{
+  const uint32_t size = 1u << bitlen, mask = size - 1;
+  uint32_t index        = key & mask;
+  const uint32_t stride = (key >> bitlen) * 2 + 1;
+  for (uint32_t i = 0; i < size; ++i) {
+    const uint32_t old = atomicCAS(&table[index], kInvalid, key);
+    if (old == kInvalid) return 1;
+    if (old == key) return 0;
+    index = (index + stride) & mask;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t dist_key(float d)
+{
+  uint32_t u = __float_as_uint(d);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_dist(uint32_t k)
+{
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// Bitonic sort of 32*E 64-bit keys held E per lane, striped (element index i = e*32 + lane), ascending.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[E], int lane)
+{
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int es = stride >> 5;  // partner element offset inside the lane
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & es) == 0) {
+            const int i   = e * 32 + lane;
+            const bool up = (i & size) == 0;
+            uint64_t a = k[e], b = k[e | es];
+            if ((a > b) == up) { k[e] = b; k[e | es] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int i        = e * 32 + lane;
+          const bool up      = (i & size) == 0;
+          const bool lower   = (lane & stride) == 0;
+          const uint64_t o   = __shfl_xor_sync(0xffffffffu, k[e], stride);
+          const bool take_min = (lower == up);
+          k[e] = take_min ? (k[e] < o ? k[e] : o) : (k[e] > o ? k[e] : o);
+        }
+      }
+    }
+  }
+}
+
+struct cagra_launch {
+  const float* data;
+  const uint32_t* graph;
+  int64_t n;
+  int dim, ld, degree;
+  const float* queries;
+  int64_t nq;
+  int metric;  // L2Expanded or InnerProduct
+  int k, itopk, search_width, min_iter, max_iter;
+  uint32_t hash_bitlen, small_hash_bitlen, reset_interval;
+  int num_random_samplings;
+  uint64_t rand_xor_mask;
+  uint32_t* hash_global;  // used when small_hash_bitlen == 0
+  uint32_t* out_idx32;
+  int64_t* out_idx64;
+  float* out_dist;
+  uint32_t* out_iters;
+};
+
+// squared L2 / negative dot between the smem query and a dataset row, computed by a team of 8 lanes
+__device__ __forceinline__ float team_distance(const float* __restrict__ row, const float* __restrict__ sq, int dim, int t, bool ip)
+{
+  float acc = 0.f;
+  // 16-byte chunks, chunk c handled by team lane c % 8
+  const int n_chunks = dim >> 2;
+  for (int c = t; c < n_chunks; c += 8) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(row) + c);
+    const float4 q = reinterpret_cast<const float4*>(sq)[c];
+    if (ip) {
+      acc = fmaf(-q.x, x.x, acc); acc = fmaf(-q.y, x.y, acc); acc = fmaf(-q.z, x.z, acc); acc = fmaf(-q.w, x.w, acc);
+    } else {
+      float d0 = q.x - x.x, d1 = q.y - x.y, d2 = q.z - x.z, d3 = q.w - x.w;
+      acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+    }
+  }
+  for (int j = (n_chunks << 2) + t; j < dim; j += 8) {  // tail when dim % 4 != 0
+    const float x = row[j], q = sq[j];
+    if (ip) acc = fmaf(-q, x, acc);
+    else { float df = q - x; acc = fmaf(df, df, acc); }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  return acc;
+}
+
+// EI = itopk / 32, EC = (search_width * degree rounded up to 32) / 32 ; buffer = EI + EC keys per lane
+template <int EI, int EC>
+__global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
+{
+  constexpr int EB = EI + EC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = static_cast<int64_t>(blockIdx.x) * warps + wid;
+  const bool ip    = p.metric == InnerProduct;
+  const int qpad   = (p.dim + 3) & ~3;
+  const uint32_t small_size = p.small_hash_bitlen ? (1u << p.small_hash_bitlen) : 0u;
+  const int n_cand = p.search_width * p.degree;
+  // per-warp shared memory: query | hash (small) | staged ids | staged distances | parents
+  const size_t per_warp = static_cast<size_t>(qpad) * 4 + static_cast<size_t>(small_size) * 4 + static_cast<size_t>(EB * 32) * 8 + 16;
+  unsigned char* base   = smem_raw + per_warp * wid;
+  float* sq             = reinterpret_cast<float*>(base);
+  uint32_t* shash       = reinterpret_cast<uint32_t*>(sq + qpad);
+  uint32_t* scand       = shash + small_size;
+  float* sdist          = reinterpret_cast<float*>(scand + EB * 32);
+  uint32_t* sparent     = reinterpret_cast<uint32_t*>(sdist + EB * 32);
+  if (qi >= p.nq) return;
+
+  const uint32_t bitlen = p.small_hash_bitlen ? p.small_hash_bitlen : p.hash_bitlen;
+  uint32_t* table       = p.small_hash_bitlen ? shash : p.hash_global + (static_cast<size_t>(qi) << p.hash_bitlen);
+  const uint32_t tsize  = 1u << bitlen;
+  for (int j = lane; j < qpad; j += 32) sq[j] = j < p.dim ? p.queries[qi * p.dim + j] : 0.f;
+  for (uint32_t j = lane; j < tsize; j += 32) table[j] = kInvalid;
+  __syncwarp();
+
+  const int t = lane & 7, g = lane >> 3;  // team lane / team id (4 teams of 8)
+  uint64_t key[EB];
+
+  // ---- random seeds over the whole buffer (device_common_jit.cuh:36-112)
+  const int buf = p.itopk + n_cand;
+#pragma unroll
+  for (int e = 0; e < EB; ++e) key[e] = ~0ull;
+  for (int i0 = 0; i0 < EB * 32; i0 += 4) {
+    const int i        = i0 + g;  // buffer slot handled by this team
+    const bool valid_i = i < buf;
+    float best         = INFINITY;
+    uint32_t best_id   = kInvalid;
+    if (i0 < buf) {  // warp-uniform: at least one team has work
+      for (int j = 0; j < p.num_random_samplings; ++j) {
+        uint32_t seed = 0;
+        if (valid_i) {
+          const uint64_t gid = static_cast<uint64_t>(i) + static_cast<uint64_t>(buf) * static_cast<uint64_t>(j);
+          seed               = static_cast<uint32_t>(xorshift64(gid ^ p.rand_xor_mask) % static_cast<uint64_t>(p.n));
+        }
+        const float dd = team_distance(p.data + static_cast<int64_t>(seed) * p.ld, sq, p.dim, t, ip);
+        if (valid_i && dd < best) { best = dd; best_id = seed; }
+      }
+    }
+    if (t == 0) {
+      if (best_id != kInvalid && hash_insert(table, bitlen, best_id) == 0) { best = INFINITY; best_id = kInvalid; }
+      scand[i] = best_id;
+      sdist[i] = best;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < EB; ++e) {
+    const int idx     = e * 32 + lane;
+    const uint32_t id = scand[idx];
+    key[e] = id == kInvalid ? ~0ull : (static_cast<uint64_t>(dist_key(sdist[idx])) << 32) | id;
+  }
+  __syncwarp();
+
+  uint32_t iter = 0;
+  while (true) {
+    if (p.small_hash_bitlen && (iter + 1) % p.reset_interval == 0) {
+      for (uint32_t j = lane; j < tsize; j += 32) table[j] = kInvalid;
+      __syncwarp();
+    }
+    // ---- keep the itopk best of (itopk U candidates), sorted: keys 0..EI-1 after the sort
+    warp_bitonic_sort<EB>(key, lane);
+    if (static_cast<int>(iter + 1) == p.max_iter) break;
+
+    // ---- pick up to search_width unvisited parents, in rank order (search_single_cta_device_helpers.cuh:97-137)
+    int n_parents = 0;  // search_width <= 4 supported by this kernel; ids staged in sparent[]
+#pragma unroll
+    for (int e = 0; e < EI; ++e) {
+      const uint32_t id   = static_cast<uint32_t>(key[e]);
+      const bool unvisited = (key[e] != ~0ull) && (id & kMsb) == 0;
+      uint32_t m = __ballot_sync(0xffffffffu, unvisited);
+      while (m && n_parents < p.search_width) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t pid = __shfl_sync(0xffffffffu, id, src);
+        if (lane == src) key[e] |= kMsb;  // mark as used
+        if (lane == 0) sparent[n_parents] = pid;
+        ++n_parents;
+      }
+    }
+    // ---- restore the small hash with the current itopk (after a reset)
+    if (p.small_hash_bitlen && (iter + 1) % p.reset_interval == 0) {
+#pragma unroll
+      for (int e = 0; e < EI; ++e)
+        if (key[e] != ~0ull) hash_insert(table, bitlen, static_cast<uint32_t>(key[e]) & ~kMsb);
+      __syncwarp();
+    }
+    if (n_parents == 0 && static_cast<int>(iter) >= p.min_iter) break;
+
+    // ---- children of the parents: adjacency rows, dedup through the hash, compact the survivors
+    int n_new = 0;
+    __syncwarp();
+    for (int pi = 0; pi < n_parents; ++pi) {
+      const uint32_t parent = sparent[pi];
+      for (int j0 = 0; j0 < p.degree; j0 += 32) {
+        const int j    = j0 + lane;
+        uint32_t child = kInvalid;
+        if (j < p.degree) child = __ldg(p.graph + static_cast<int64_t>(parent) * p.degree + j);
+        bool fresh = false;
+        if (child != kInvalid && child < static_cast<uint32_t>(p.n)) fresh = hash_insert(table, bitlen, child) != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+        if (fresh) scand[n_new + __popc(m & ((1u << lane) - 1u))] = child;
+        n_new += __popc(m);
+      }
+    }
+    __syncwarp();
+    // ---- distances: 4 candidates per step (teams of 8 lanes), two steps in flight
+    for (int c0 = 0; c0 < n_new; c0 += 8) {
+      const int ca = c0 + g, cb = c0 + 4 + g;
+      const uint32_t ida = ca < n_new ? scand[ca] : 0u, idb = cb < n_new ? scand[cb] : 0u;
+      const float da = team_distance(p.data + static_cast<int64_t>(ida) * p.ld, sq, p.dim, t, ip);
+      const float db = team_distance(p.data + static_cast<int64_t>(idb) * p.ld, sq, p.dim, t, ip);
+      if (t == 0) {
+        if (ca < n_new) sdist[ca] = da;
+        if (cb < n_new) sdist[cb] = db;
+      }
+    }
+    __syncwarp();
+    // ---- candidates -> register keys EI..EB-1
+#pragma unroll
+    for (int e = 0; e < EC; ++e) {
+      const int c = e * 32 + lane;
+      key[EI + e] = c < n_new ? (static_cast<uint64_t>(dist_key(sdist[c])) << 32) | scand[c] : ~0ull;
+    }
+    __syncwarp();
+    ++iter;
+  }
+
+  // ---- results: first k entries of the sorted list
+#pragma unroll
+  for (int e = 0; e < EI; ++e) {
+    const int r = e * 32 + lane;
+    if (r < p.k) {
+      const bool valid  = key[e] != ~0ull;
+      const uint32_t id = valid ? (static_cast<uint32_t>(key[e]) & ~kMsb) : kInvalid;
+      float d           = valid ? key_dist(static_cast<uint32_t>(key[e] >> 32)) : FLT_MAX;
+      if (valid && ip) d = -d;
+      if (p.out_idx32) p.out_idx32[qi * p.k + r] = id;
+      if (p.out_idx64) p.out_idx64[qi * p.k + r] = valid ? static_cast<int64_t>(id) : -1;  // reference: max u32 cast
+      p.out_dist[qi * p.k + r] = d;
+    }
+  }
+  if (p.out_iters && lane == 0) p.out_iters[qi] = iter + 1;
+}
+
+struct cagra_plan {
+  int itopk, max_iter, min_iter;
+  uint32_t hash_bitlen, small_hash_bitlen, reset_interval;
+};
+
+// search_plan.cuh:199-372 (single-CTA branch)
+cagra_plan make_plan(const cuvsCagraSearchParams& sp, int64_t n, int degree, int k)
+{
+  cagra_plan pl{};
+  size_t itopk = sp.itopk_size ? sp.itopk_size : 64;
+  if (itopk % 32) itopk += 32 - itopk % 32;
+  const size_t w = std::max<size_t>(sp.search_width, 1);
+  size_t mi = sp.max_iterations;
+  if (mi == 0) {
+    mi = itopk / w;
+    int64_t reach = 1;
+    while (reach < n) { reach *= std::max<int64_t>(2, degree / 2); ++mi; }
+  }
+  mi = std::max(mi, sp.min_iterations);
+  pl.itopk = static_cast<int>(itopk);
+  pl.max_iter = static_cast<int>(mi);
+  pl.min_iter = static_cast<int>(sp.min_iterations);
+  const float fill = sp.hashmap_max_fill_rate > 0.f ? sp.hashmap_max_fill_rate : 0.5f;
+  pl.hash_bitlen = pl.small_hash_bitlen = 0;
+  pl.reset_interval = 1u << 20;
+  if (sp.hashmap_mode == AUTO_HASH || sp.hashmap_mode == SMALL) {
+    const size_t max_visited = itopk + w * degree;
+    uint32_t hb = std::max<uint32_t>(8, static_cast<uint32_t>(sp.hashmap_min_bitlen));
+    while (max_visited > (size_t(1) << hb) * fill) ++hb;
+    if (hb <= 13) {
+      pl.small_hash_bitlen = pl.hash_bitlen = hb;
+      pl.reset_interval = 1;
+      while (itopk + w * degree * (pl.reset_interval + 1) <= (size_t(1) << hb) * fill) ++pl.reset_interval;
+    } else {
+      B2_EXPECTS(sp.hashmap_mode == AUTO_HASH, "small-hash cannot be used because the required hash size exceeds the limit (%u)", 1u << 13);
+    }
+  }
+  if (pl.hash_bitlen == 0) {
+    const size_t max_visited = itopk + w * degree * mi;
+    uint32_t hb = std::max<uint32_t>(11, static_cast<uint32_t>(sp.hashmap_min_bitlen));
+    while (max_visited > (size_t(1) << hb) * fill) ++hb;
+    B2_EXPECTS(hb <= 20, "hash_bitlen cannot be largen than 20 (1M). You can decrease itopk_size, search_width or max_iterations to reduce the required hashmap size.");
+    pl.hash_bitlen = hb;
+  }
+  B2_EXPECTS(k <= pl.itopk, "topk = %d must be smaller than itopk_size = %d", k, pl.itopk);
+  return pl;
+}
+
+template <int EI, int EC>
+void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
+{
+  auto kern = cagra_search_kernel<EI, EC>;
+  int warps = 16;
+  while (warps > 1 && per_warp_smem * warps > 200 * 1024) warps >>= 1;
+  const size_t smem = per_warp_smem * warps;
+  B2_EXPECTS(per_warp_smem <= 200 * 1024, "cagra search: per-query shared memory (%zu bytes) exceeds the limit", per_warp_smem);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  timed_section ts("cagra_search", s);
+  count_launch();
+  kern<<<blocks_for(p.nq, warps), warps * 32, smem, s>>>(p);
+  B2_CUDA(cudaGetLastError());
+}
+
+void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchParams& sp, const float* queries, int64_t nq, int k,
+                  uint32_t* out32, int64_t* out64, float* out_dist)
+{
+  auto s = res->stream;
+  if (nq == 0) return;
+  B2_EXPECTS(idx.metric == L2Expanded || idx.metric == InnerProduct || idx.metric == L2SqrtExpanded,
+             "cagra search: unsupported metric %d", int(idx.metric));
+  const cagra_plan pl = make_plan(sp, idx.n, idx.degree, k);
+  const int w         = static_cast<int>(std::max<size_t>(sp.search_width, 1));
+  B2_EXPECTS(w <= 4, "cagra search: search_width > 4 is not supported by this build (got %d)", w);
+  B2_EXPECTS(!sp.persistent, "cagra search: the persistent (latency) mode is out of scope of this library");
+  const int n_cand = w * idx.degree;
+  const int EI = pl.itopk / 32, EC = (n_cand + 31) / 32;
+  cagra_launch p{};
+  p.data = idx.data; p.graph = idx.graph; p.n = idx.n; p.dim = idx.dim; p.ld = idx.ld; p.degree = idx.degree;
+  p.queries = queries; p.nq = nq; p.metric = idx.metric == InnerProduct ? InnerProduct : L2Expanded;
+  p.k = k; p.itopk = pl.itopk; p.search_width = w; p.min_iter = pl.min_iter; p.max_iter = pl.max_iter;
+  p.hash_bitlen = pl.hash_bitlen; p.small_hash_bitlen = pl.small_hash_bitlen; p.reset_interval = pl.reset_interval;
+  p.num_random_samplings = static_cast<int>(std::max<uint32_t>(sp.num_random_samplings, 1));
+  p.rand_xor_mask = sp.rand_xor_mask;
+  p.out_idx32 = out32; p.out_idx64 = out64; p.out_dist = out_dist; p.out_iters = nullptr;
+  dbuf<uint32_t> gh;
+  if (pl.small_hash_bitlen == 0) {
+    gh.alloc(static_cast<size_t>(nq) << pl.hash_bitlen, s);
+    p.hash_global = gh.data();
+  }
+  const int qpad = (idx.dim + 3) & ~3;
+  const size_t per_warp = static_cast<size_t>(qpad) * 4 + (pl.small_hash_bitlen ? (size_t(4) << pl.small_hash_bitlen) : 0) +
+                          static_cast<size_t>(EI + EC) * 32 * 8 + 16;
+#define B2_CAGRA_CASE(EI_, EC_) if (EI == EI_ && EC == EC_) { launch_search<EI_, EC_>(s, p, per_warp); launched = true; }
+  bool launched = false;
+  B2_CAGRA_CASE(1, 1) B2_CAGRA_CASE(1, 2) B2_CAGRA_CASE(1, 4)
+  B2_CAGRA_CASE(2, 1) B2_CAGRA_CASE(2, 2) B2_CAGRA_CASE(2, 4)
+  B2_CAGRA_CASE(4, 1) B2_CAGRA_CASE(4, 2) B2_CAGRA_CASE(4, 4)
+  B2_CAGRA_CASE(8, 2) B2_CAGRA_CASE(8, 4)
+#undef B2_CAGRA_CASE
+  B2_EXPECTS(launched, "cagra search: unsupported (itopk=%d, search_width*graph_degree=%d) combination; itopk in {32,64,128,256} and "
+                       "search_width*degree in {<=32, <=64, <=128} are built", pl.itopk, n_cand);
+  if (idx.metric == L2SqrtExpanded) postprocess_distances(s, out_dist, nq * k, L2SqrtExpanded);
+}
+
+// ------------------------------------------------------------------ graph build (kNN + reverse edges)
+__global__ void knn_to_graph_kernel(const int64_t* __restrict__ knn, int64_t n, int kk, int keep, uint32_t* __restrict__ graph, int degree)
+{
+  // forward half: the `keep` nearest neighbours (self removed)
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int w = 0;
+  for (int j = 0; j < kk && w < degree; ++j) {
+    int64_t v = knn[i * kk + j];
+    if (v == i || v < 0 || v >= n) continue;
+    graph[i * degree + w] = static_cast<uint32_t>(v);
+    ++w;
+  }
+  for (; w < degree; ++w) graph[i * degree + w] = static_cast<uint32_t>((i + 1 + w) % n);  // degenerate tiny inputs
+  (void)keep;
+}
+
+__global__ void reverse_edges_kernel(const uint32_t* __restrict__ fwd, int64_t n, int degree, int keep, uint32_t* __restrict__ rev,
+                                     uint32_t* __restrict__ rev_cnt, int rev_cap)
+{
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= n * keep) return;
+  int64_t u = t / keep;
+  int r     = static_cast<int>(t % keep);
+  uint32_t v = fwd[u * degree + r];
+  uint32_t slot = atomicAdd(&rev_cnt[v], 1u);
+  if (slot < static_cast<uint32_t>(rev_cap)) rev[static_cast<int64_t>(v) * rev_cap + slot] = static_cast<uint32_t>(u);
+}
+
+// final row = first `keep` forward edges, then reverse edges not already present, then remaining forward edges
+__global__ void merge_graph_kernel(const uint32_t* __restrict__ fwd, const uint32_t* __restrict__ rev, const uint32_t* __restrict__ rev_cnt,
+                                   int64_t n, int degree, int keep, int rev_cap, uint32_t* __restrict__ out)
+{
+  int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (u >= n) return;
+  const uint32_t* f = fwd + u * degree;
+  uint32_t* o       = out + u * degree;
+  int w = 0;
+  for (; w < keep; ++w) o[w] = f[w];
+  const int nr = min(static_cast<int>(rev_cnt[u]), rev_cap);
+  for (int j = 0; j < nr && w < degree; ++j) {
+    uint32_t v = rev[u * rev_cap + j];
+    bool dup = false;
+    for (int q = 0; q < w; ++q) dup |= (o[q] == v);
+    if (!dup && v != u) o[w++] = v;
+  }
+  for (int j = keep; j < degree && w < degree; ++j) {
+    uint32_t v = f[j];
+    bool dup = false;
+    for (int q = 0; q < w; ++q) dup |= (o[q] == v);
+    if (!dup) o[w++] = v;
+  }
+  for (int j = 0; w < degree; ++j) {  // pathological duplicates: fill with successive ids
+    uint32_t v = static_cast<uint32_t>((u + 1 + j) % n);
+    bool dup = false;
+    for (int q = 0; q < w; ++q) dup |= (o[q] == v);
+    if (!dup && v != u) o[w++] = v;
+  }
+}
+
+}  // namespace
+
+// exact kNN graph through the library's own brute-force search (C boundary re-used internally)
+static void build_knn_graph(cuvsResources_t res_h, resources* res, const float* data, int64_t n, int dim, cuvsDistanceType metric,
+                            int kk, int64_t* knn_out)
+{
+  cuvsBruteForceIndex_t bf = nullptr;
+  B2_EXPECTS(cuvsBruteForceIndexCreate(&bf) == CUVS_SUCCESS, "brute force index create failed");
+  int64_t shape[2] = {n, dim};
+  DLManagedTensor ds{};
+  ds.dl_tensor.data = const_cast<float*>(data); ds.dl_tensor.device = DLDevice{kDLCUDA, res->device}; ds.dl_tensor.ndim = 2;
+  ds.dl_tensor.dtype = DLDataType{kDLFloat, 32, 1}; ds.dl_tensor.shape = shape;
+  cuvsDistanceType m = metric == InnerProduct ? InnerProduct : L2Expanded;
+  if (cuvsBruteForceBuild(res_h, &ds, m, 2.0f, bf) != CUVS_SUCCESS) {
+    std::string e = cuvsGetLastErrorText() ? cuvsGetLastErrorText() : "?";
+    cuvsBruteForceIndexDestroy(bf);
+    B2_FAIL("cagra build: kNN stage failed: %s", e.c_str());
+  }
+  const int64_t chunk = 16384;
+  dbuf<float> dist(static_cast<size_t>(chunk) * kk, res->stream);
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    int64_t rows = std::min(chunk, n - r0);
+    int64_t qs[2] = {rows, dim}, os[2] = {rows, kk};
+    DLManagedTensor q = ds, nb{}, dd{};
+    q.dl_tensor.data = const_cast<float*>(data) + r0 * dim; q.dl_tensor.shape = qs;
+    nb.dl_tensor.data = knn_out + r0 * kk; nb.dl_tensor.device = ds.dl_tensor.device; nb.dl_tensor.ndim = 2;
+    nb.dl_tensor.dtype = DLDataType{kDLInt, 64, 1}; nb.dl_tensor.shape = os;
+    dd = nb; dd.dl_tensor.data = dist.data(); dd.dl_tensor.dtype = DLDataType{kDLFloat, 32, 1};
+    if (cuvsBruteForceSearch(res_h, bf, &q, &nb, &dd, cuvsFilter{0, NO_FILTER}) != CUVS_SUCCESS) {
+      std::string e = cuvsGetLastErrorText() ? cuvsGetLastErrorText() : "?";
+      cuvsBruteForceIndexDestroy(bf);
+      B2_FAIL("cagra build: kNN stage failed: %s", e.c_str());
+    }
+  }
+  B2_CUDA(cudaStreamSynchronize(res->stream));
+  cuvsBruteForceIndexDestroy(bf);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static cagra_index& cagra_of(cuvsCagraIndex_t index)
+{
+  B2_EXPECTS(index != nullptr && index->addr != 0, "index is not built");
+  return *reinterpret_cast<cagra_index*>(index->addr);
+}
+
+static void set_dataset(resources* r, cagra_index& idx, const DLTensor& ds)
+{
+  B2_EXPECTS(dl_is(ds, kDLFloat, 32), "cagra: only float32 datasets are supported by this build");
+  B2_EXPECTS(ds.ndim == 2 && dl_is_c_contiguous(ds), "dataset must be a row-major 2-D tensor");
+  idx.n   = ds.shape[0];
+  idx.dim = static_cast<int>(ds.shape[1]);
+  idx.ld  = (idx.dim + 3) & ~3;  // rows padded to 16 bytes (cagra.hpp:610)
+  const bool dev = dl_is_device(ds) && ds.device.device_type != kDLCUDAHost;
+  if (dev && idx.ld == idx.dim && (reinterpret_cast<uintptr_t>(dl_ptr<float>(ds)) & 15) == 0) {
+    idx.data = dl_ptr<float>(ds);  // non-owning view, like the reference's strided_dataset view
+  } else {
+    idx.data_own.alloc(static_cast<size_t>(idx.n) * idx.ld);
+    B2_CUDA(cudaMemsetAsync(idx.data_own.data(), 0, sizeof(float) * idx.n * idx.ld, r->stream));
+    B2_CUDA(cudaMemcpy2DAsync(idx.data_own.data(), sizeof(float) * idx.ld, dl_ptr<float>(ds), sizeof(float) * idx.dim,
+                              sizeof(float) * idx.dim, idx.n, cudaMemcpyDefault, r->stream));
+    idx.data = idx.data_own.data();
+  }
+}
+
+extern "C" {
+
+cuvsError_t cuvsCagraIndexParamsCreate(cuvsCagraIndexParams_t* params)
+{
+  return guarded([=] {
+    B2_EXPECTS(params != nullptr, "params is null");
+    // c/src/neighbors/cagra.cpp:733-742
+    auto p = new cuvsCagraIndexParams{};
+    p->metric = L2Expanded; p->intermediate_graph_degree = 128; p->graph_degree = 64; p->build_algo = IVF_PQ; p->nn_descent_niter = 20;
+    p->compression = nullptr;
+    p->graph_build_params = new cuvsIvfPqParams{nullptr, nullptr, 1};
+    *params = p;
+  });
+}
+cuvsError_t cuvsCagraIndexParamsDestroy(cuvsCagraIndexParams_t params)
+{
+  return guarded([=] {
+    if (!params) return;
+    if (params->graph_build_params) {
+      if (params->build_algo == ACE) delete static_cast<cuvsAceParams*>(params->graph_build_params);
+      else delete static_cast<cuvsIvfPqParams*>(params->graph_build_params);
+    }
+    delete params;
+  });
+}
+cuvsError_t cuvsCagraCompressionParamsCreate(cuvsCagraCompressionParams_t* params)
+{
+  return guarded([=] { *params = new cuvsCagraCompressionParams{8, 0, 0, 25, 0.0, 0.0}; });
+}
+cuvsError_t cuvsCagraCompressionParamsDestroy(cuvsCagraCompressionParams_t params) { return guarded([=] { delete params; }); }
+cuvsError_t cuvsAceParamsCreate(cuvsAceParams_t* params)
+{
+  return guarded([=] { *params = new cuvsAceParams{0, 120, "/tmp/ace_build", false, 0.0, 0.0}; });
+}
+cuvsError_t cuvsAceParamsDestroy(cuvsAceParams_t params) { return guarded([=] { delete params; }); }
+cuvsError_t cuvsCagraIndexParamsFromHnswParams(cuvsCagraIndexParams_t params, int64_t, int64_t, int M, int, enum cuvsCagraHnswHeuristicType heuristic,
+                                               cuvsDistanceType metric)
+{
+  return guarded([=] {
+    B2_EXPECTS(params != nullptr, "params is null");
+    params->metric       = metric;
+    params->graph_degree = heuristic == CUVS_CAGRA_HEURISTIC_SAME_GRAPH_FOOTPRINT ? static_cast<size_t>(2 * M) : static_cast<size_t>(std::max(2 * M, 32));
+    params->intermediate_graph_degree = params->graph_degree * 2;
+  });
+}
+cuvsError_t cuvsCagraExtendParamsCreate(cuvsCagraExtendParams_t* params) { return guarded([=] { *params = new cuvsCagraExtendParams{0}; }); }
+cuvsError_t cuvsCagraExtendParamsDestroy(cuvsCagraExtendParams_t params) { return guarded([=] { delete params; }); }
+
+cuvsError_t cuvsCagraSearchParamsCreate(cuvsCagraSearchParams_t* params)
+{
+  return guarded([=] {
+    B2_EXPECTS(params != nullptr, "params is null");
+    // c/src/neighbors/cagra.cpp:848-861 (unset fields are zero; algo 0 = SINGLE_CTA, hashmap_mode 0 = HASH as there)
+    auto p = new cuvsCagraSearchParams{};
+    p->itopk_size = 64; p->search_width = 1; p->hashmap_max_fill_rate = 0.5f; p->num_random_samplings = 1;
+    p->rand_xor_mask = 0x128394; p->persistent = false; p->persistent_lifetime = 2; p->persistent_device_usage = 1.0f;
+    p->hashmap_mode = AUTO_HASH; p->algo = AUTO;
+    *params = p;
+  });
+}
+cuvsError_t cuvsCagraSearchParamsDestroy(cuvsCagraSearchParams_t params) { return guarded([=] { delete params; }); }
+
+cuvsError_t cuvsCagraIndexCreate(cuvsCagraIndex_t* index)
+{
+  return guarded([=] {
+    B2_EXPECTS(index != nullptr, "index is null");
+    *index = new cuvsCagraIndex{};
+  });
+}
+cuvsError_t cuvsCagraIndexDestroy(cuvsCagraIndex_t index)
+{
+  return guarded([=] {
+    if (!index) return;
+    delete reinterpret_cast<cagra_index*>(index->addr);
+    delete index;
+  });
+}
+cuvsError_t cuvsCagraIndexGetDims(cuvsCagraIndex_t index, int64_t* dim) { return guarded([=] { *dim = cagra_of(index).dim; }); }
+cuvsError_t cuvsCagraIndexGetSize(cuvsCagraIndex_t index, int64_t* size) { return guarded([=] { *size = cagra_of(index).n; }); }
+cuvsError_t cuvsCagraIndexGetGraphDegree(cuvsCagraIndex_t index, int64_t* d) { return guarded([=] { *d = cagra_of(index).degree; }); }
+cuvsError_t cuvsCagraIndexGetDataset(cuvsCagraIndex_t index, DLManagedTensor* dataset)
+{
+  return guarded([=] {
+    auto& idx        = cagra_of(index);
+    int64_t shape[2] = {idx.n, idx.dim};
+    dl_fill_view(dataset, const_cast<float*>(idx.data), idx.device, DLDataType{kDLFloat, 32, 1}, 2, shape);
+    if (idx.ld != idx.dim) {
+      dataset->dl_tensor.strides    = new int64_t[2];
+      dataset->dl_tensor.strides[0] = idx.ld;
+      dataset->dl_tensor.strides[1] = 1;
+      dataset->deleter = [](DLManagedTensor* self) {
+        delete[] self->dl_tensor.shape; delete[] self->dl_tensor.strides;
+        self->dl_tensor.shape = nullptr; self->dl_tensor.strides = nullptr;
+      };
+    }
+  });
+}
+cuvsError_t cuvsCagraIndexGetGraph(cuvsCagraIndex_t index, DLManagedTensor* graph)
+{
+  return guarded([=] {
+    auto& idx        = cagra_of(index);
+    int64_t shape[2] = {idx.n, idx.degree};
+    dl_fill_view(graph, const_cast<uint32_t*>(idx.graph), idx.device, DLDataType{kDLUInt, 32, 1}, 2, shape);
+  });
+}
+
+cuvsError_t cuvsCagraIndexFromArgs(cuvsResources_t res, cuvsDistanceType metric, DLManagedTensor* graph_t, DLManagedTensor* dataset_t,
+                                   cuvsCagraIndex_t index)
+{
+  return guarded([=] {
+    auto r = as_res(res);
+    B2_EXPECTS(graph_t && dataset_t && index, "null argument");
+    const DLTensor& g = graph_t->dl_tensor;
+    B2_EXPECTS(dl_is(g, kDLUInt, 32) && g.ndim == 2 && dl_is_c_contiguous(g), "graph must be a row-major uint32 matrix");
+    auto idx    = std::make_unique<cagra_index>();
+    idx->device = r->device;
+    idx->metric = metric;
+    set_dataset(r, *idx, dataset_t->dl_tensor);
+    B2_EXPECTS(g.shape[0] == idx->n, "graph rows (%lld) != dataset rows (%lld)", (long long)g.shape[0], (long long)idx->n);
+    B2_EXPECTS(idx->n < (int64_t(1) << 31), "cagra: at most 2^31 - 1 rows (the index MSB flags visited parents)");
+    idx->degree = static_cast<int>(g.shape[1]);
+    if (dl_is_device(g) && g.device.device_type != kDLCUDAHost) idx->graph = dl_ptr<uint32_t>(g);
+    else {
+      idx->graph_own.alloc(static_cast<size_t>(idx->n) * idx->degree);
+      B2_CUDA(cudaMemcpyAsync(idx->graph_own.data(), dl_ptr<uint32_t>(g), sizeof(uint32_t) * idx->n * idx->degree, cudaMemcpyDefault, r->stream));
+      idx->graph = idx->graph_own.data();
+    }
+    B2_CUDA(cudaStreamSynchronize(r->stream));
+    if (index->addr) delete reinterpret_cast<cagra_index*>(index->addr);
+    index->addr  = reinterpret_cast<uintptr_t>(idx.release());
+    index->dtype = DLDataType{kDLFloat, 32, 1};
+  });
+}
+
+cuvsError_t cuvsCagraBuild(cuvsResources_t res, cuvsCagraIndexParams_t params, DLManagedTensor* dataset_t, cuvsCagraIndex_t index)
+{
+  return guarded([=] {
+    auto r = as_res(res);
+    B2_EXPECTS(params && dataset_t && index, "null argument");
+    B2_EXPECTS(params->compression == nullptr, "cagra build: VPQ compression is out of scope of this library");
+    auto idx    = std::make_unique<cagra_index>();
+    idx->device = r->device;
+    idx->metric = params->metric;
+    set_dataset(r, *idx, dataset_t->dl_tensor);
+    const int64_t n = idx->n;
+    B2_EXPECTS(n >= 2 && n < (int64_t(1) << 31), "cagra build: dataset size out of range");
+    const int degree = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(params->graph_degree), n - 1));
+    B2_EXPECTS(degree >= 1, "graph_degree must be >= 1");
+    // kNN stage (exact; the library's own scan) — k capped by what the fused top-k supports per call
+    const int kk = static_cast<int>(std::min<int64_t>(n, std::min<int64_t>(degree + 1, 24)));
+    dbuf<float> compact;
+    const float* data = idx->data;
+    if (idx->ld != idx->dim) {  // brute force wants unpadded rows
+      compact.alloc(static_cast<size_t>(n) * idx->dim, r->stream);
+      B2_CUDA(cudaMemcpy2DAsync(compact.data(), sizeof(float) * idx->dim, idx->data, sizeof(float) * idx->ld, sizeof(float) * idx->dim, n,
+                                cudaMemcpyDeviceToDevice, r->stream));
+      data = compact.data();
+    }
+    dbuf<int64_t> knn(static_cast<size_t>(n) * kk, r->stream);
+    build_knn_graph(res, r, data, n, idx->dim, idx->metric, kk, knn.data());
+    // forward edges, then reverse-edge augmentation up to `degree`
+    dbuf<uint32_t> fwd(static_cast<size_t>(n) * degree, r->stream);
+    const int keep = std::min(kk - 1 > 0 ? kk - 1 : 1, std::max(1, degree / 2));
+    count_launch(3);
+    knn_to_graph_kernel<<<blocks_for(n, 128), 128, 0, r->stream>>>(knn.data(), n, kk, keep, fwd.data(), degree);
+    const int rev_cap = degree;
+    dbuf<uint32_t> rev(static_cast<size_t>(n) * rev_cap, r->stream), rev_cnt(static_cast<size_t>(n), r->stream);
+    B2_CUDA(cudaMemsetAsync(rev_cnt.data(), 0, sizeof(uint32_t) * n, r->stream));
+    reverse_edges_kernel<<<blocks_for(n * keep, 256), 256, 0, r->stream>>>(fwd.data(), n, degree, keep, rev.data(), rev_cnt.data(), rev_cap);
+    idx->graph_own.alloc(static_cast<size_t>(n) * degree);
+    merge_graph_kernel<<<blocks_for(n, 128), 128, 0, r->stream>>>(fwd.data(), rev.data(), rev_cnt.data(), n, degree, keep, rev_cap, idx->graph_own.data());
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaStreamSynchronize(r->stream));
+    idx->graph  = idx->graph_own.data();
+    idx->degree = degree;
+    if (index->addr) delete reinterpret_cast<cagra_index*>(index->addr);
+    index->addr  = reinterpret_cast<uintptr_t>(idx.release());
+    index->dtype = DLDataType{kDLFloat, 32, 1};
+  });
+}
+
+cuvsError_t cuvsCagraSearch(cuvsResources_t res, cuvsCagraSearchParams_t params, cuvsCagraIndex_t index, DLManagedTensor* queries_t,
+                            DLManagedTensor* neighbors_t, DLManagedTensor* distances_t, cuvsFilter filter)
+{
+  return guarded([=] {
+    auto r = as_res(res);
+    B2_EXPECTS(params && queries_t && neighbors_t && distances_t, "null argument");
+    auto& idx = cagra_of(index);
+    const DLTensor& queries   = queries_t->dl_tensor;
+    const DLTensor& neighbors = neighbors_t->dl_tensor;
+    const DLTensor& distances = distances_t->dl_tensor;
+    // checks as in c/src/neighbors/cagra.cpp:646-690
+    B2_EXPECTS(dl_is_device(queries), "queries should have device compatible memory");
+    B2_EXPECTS(dl_is_device(neighbors), "neighbors should have device compatible memory");
+    B2_EXPECTS(dl_is_device(distances), "distances should have device compatible memory");
+    B2_EXPECTS(dl_is(neighbors, kDLUInt, 32) || dl_is(neighbors, kDLInt, 64), "neighbors should be of type uint32_t or int64_t");
+    B2_EXPECTS(dl_is(distances, kDLFloat, 32), "distances should be of type float32");
+    B2_EXPECTS(queries.dtype.code == index->dtype.code && queries.dtype.bits == index->dtype.bits, "type mismatch between index and queries");
+    B2_EXPECTS(queries.ndim == 2 && neighbors.ndim == 2 && distances.ndim == 2, "queries/neighbors/distances must be 2-D");
+    B2_EXPECTS(dl_is_c_contiguous(queries) && dl_is_c_contiguous(neighbors) && dl_is_c_contiguous(distances), "tensors must be row-major contiguous");
+    B2_EXPECTS(queries.shape[1] == idx.dim, "queries dim (%lld) != index dim (%d)", (long long)queries.shape[1], idx.dim);
+    B2_EXPECTS(neighbors.shape[0] == queries.shape[0] && distances.shape[0] == queries.shape[0] && distances.shape[1] == neighbors.shape[1], "neighbors/distances shape mismatch");
+    B2_EXPECTS(filter.type == NO_FILTER, "cagra search: pre-filters are not supported by this build yet");
+    const bool u32 = dl_is(neighbors, kDLUInt, 32);
+    cagra_search(r, idx, *params, dl_ptr<float>(queries), queries.shape[0], static_cast<int>(neighbors.shape[1]),
+                 u32 ? dl_ptr<uint32_t>(neighbors) : nullptr, u32 ? nullptr : dl_ptr<int64_t>(neighbors), dl_ptr<float>(distances));
+  });
+}
+
+// Own container (version 1): header, graph, optional dataset.
+cuvsError_t cuvsCagraSerialize(cuvsResources_t res, const char* filename, cuvsCagraIndex_t index, bool include_dataset)
+{
+  return guarded([=] {
+    auto r    = as_res(res);
+    auto& idx = cagra_of(index);
+    std::ofstream os(filename, std::ios::out | std::ios::binary);
+    B2_EXPECTS(bool(os), "Cannot open file %s", filename);
+    const char tag[4] = {'<', 'f', '4', 0};
+    os.write(tag, 4);
+    int64_t hdr[6] = {1, static_cast<int64_t>(idx.metric), idx.n, idx.dim, idx.degree, include_dataset ? 1 : 0};
+    os.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+    std::vector<uint32_t> g(static_cast<size_t>(idx.n) * idx.degree);
+    B2_CUDA(cudaMemcpyAsync(g.data(), idx.graph, g.size() * 4, cudaMemcpyDeviceToHost, r->stream));
+    B2_CUDA(cudaStreamSynchronize(r->stream));
+    os.write(reinterpret_cast<const char*>(g.data()), static_cast<std::streamsize>(g.size() * 4));
+    if (include_dataset) {
+      std::vector<float> d(static_cast<size_t>(idx.n) * idx.dim);
+      B2_CUDA(cudaMemcpy2DAsync(d.data(), sizeof(float) * idx.dim, idx.data, sizeof(float) * idx.ld, sizeof(float) * idx.dim, idx.n, cudaMemcpyDeviceToHost, r->stream));
+      B2_CUDA(cudaStreamSynchronize(r->stream));
+      os.write(reinterpret_cast<const char*>(d.data()), static_cast<std::streamsize>(d.size() * 4));
+    }
+    B2_EXPECTS(bool(os), "Error writing %s", filename);
+  });
+}
+
+cuvsError_t cuvsCagraDeserialize(cuvsResources_t res, const char* filename, cuvsCagraIndex_t index)
+{
+  return guarded([=] {
+    auto r = as_res(res);
+    B2_EXPECTS(index && filename, "null argument");
+    std::ifstream is(filename, std::ios::in | std::ios::binary);
+    B2_EXPECTS(bool(is), "Cannot open file %s", filename);
+    char tag[4]{};
+    B2_EXPECTS(bool(is.read(tag, 4)), "Invalid or truncated index header in file %s", filename);
+    B2_EXPECTS(tag[0] == '<' && tag[1] == 'f' && tag[2] == '4', "Unsupported index dtype in %s", filename);
+    int64_t hdr[6];
+    is.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
+    B2_EXPECTS(bool(is) && hdr[0] == 1, "Unsupported cagra container version in %s", filename);
+    B2_EXPECTS(hdr[5] == 1, "index file %s was saved without the dataset; use cuvsCagraIndexFromArgs to attach one", filename);
+    auto idx    = std::make_unique<cagra_index>();
+    idx->device = r->device;
+    idx->metric = static_cast<cuvsDistanceType>(hdr[1]);
+    idx->n = hdr[2]; idx->dim = static_cast<int>(hdr[3]); idx->degree = static_cast<int>(hdr[4]);
+    idx->ld = (idx->dim + 3) & ~3;
+    std::vector<uint32_t> g(static_cast<size_t>(idx->n) * idx->degree);
+    is.read(reinterpret_cast<char*>(g.data()), static_cast<std::streamsize>(g.size() * 4));
+    std::vector<float> d(static_cast<size_t>(idx->n) * idx->dim);
+    is.read(reinterpret_cast<char*>(d.data()), static_cast<std::streamsize>(d.size() * 4));
+    B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+    idx->graph_own.alloc(g.size());
+    idx->data_own.alloc(static_cast<size_t>(idx->n) * idx->ld);
+    B2_CUDA(cudaMemcpyAsync(idx->graph_own.data(), g.data(), g.size() * 4, cudaMemcpyHostToDevice, r->stream));
+    B2_CUDA(cudaMemsetAsync(idx->data_own.data(), 0, sizeof(float) * idx->n * idx->ld, r->stream));
+    B2_CUDA(cudaMemcpy2DAsync(idx->data_own.data(), sizeof(float) * idx->ld, d.data(), sizeof(float) * idx->dim, sizeof(float) * idx->dim, idx->n, cudaMemcpyHostToDevice, r->stream));
+    B2_CUDA(cudaStreamSynchronize(r->stream));
+    idx->graph = idx->graph_own.data();
+    idx->data  = idx->data_own.data();
+    if (index->addr) delete reinterpret_cast<cagra_index*>(index->addr);
+    index->addr  = reinterpret_cast<uintptr_t>(idx.release());
+    index->dtype = DLDataType{kDLFloat, 32, 1};
+  });
+}
+
+cuvsError_t cuvsCagraExtend(cuvsResources_t, cuvsCagraExtendParams_t, DLManagedTensor*, cuvsCagraIndex_t)
+{
+  return guarded([=] { B2_FAIL("cuvsCagraExtend: graph construction/extension is outside the scan+top-k hot path of this library (SURVEY §8a: build OUT OF SCOPE)"); });
+}
+cuvsError_t cuvsCagraSerializeToHnswlib(cuvsResources_t, const char*, cuvsCagraIndex_t)
+{
+  return guarded([=] { B2_FAIL("cuvsCagraSerializeToHnswlib: the hnswlib (CPU) path is out of scope of this library"); });
+}
+cuvsError_t cuvsCagraMerge(cuvsResources_t, cuvsCagraIndexParams_t, cuvsCagraIndex_t*, size_t, cuvsFilter, cuvsCagraIndex_t)
+{
+  return guarded([=] { B2_FAIL("cuvsCagraMerge: graph construction is outside the scan+top-k hot path of this library"); });
+}
+
+}  // extern "C"

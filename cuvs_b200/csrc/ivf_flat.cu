@@ -276,7 +276,7 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   const int k      = static_cast<int>(nt.shape[1]);
   B2_EXPECTS(qt.shape[1] == idx.dim, "queries dim (%lld) != index dim (%d)", (long long)qt.shape[1], idx.dim);
   B2_EXPECTS(nt.shape[0] == nq && dt.shape[0] == nq && dt.shape[1] == k, "neighbors/distances shape mismatch");
-  B2_EXPECTS(k >= 1 && k <= 32, "ivf_flat search: k must be in [1, 32] in this build (got %d)", k);
+  B2_EXPECTS(k >= 1 && k <= 64, "ivf_flat search: k must be in [1, 64] in this build (got %d)", k);
   B2_EXPECTS(n_probes >= 1, "n_probes must be >= 1");
   if (nq == 0) return;
   n_probes         = std::min<uint32_t>(n_probes, idx.n_lists);
@@ -303,6 +303,7 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   const int KC    = k <= 16 ? 16 : 32;
   const int lists = tc_lists_per_item();
   const int KCW   = KC * lists;
+  B2_EXPECTS(KCW >= k, "ivf_flat search: k = %d needs the two-list tensor-core epilogue (CUVS_B200_TC_EPIW=8)", k);
   probe_buckets pb;
   bucket_probes(res, probes.data(), nq, static_cast<int>(n_probes), idx.n_lists, idx.lists.d_offsets.data(), KCW, pb);
 

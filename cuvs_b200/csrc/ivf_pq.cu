@@ -754,7 +754,7 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   const int k      = static_cast<int>(nt.shape[1]);
   B2_EXPECTS(qt.shape[1] == idx.dim, "queries dim (%lld) != index dim (%d)", (long long)qt.shape[1], idx.dim);
   B2_EXPECTS(nt.shape[0] == nq && dt.shape[0] == nq && dt.shape[1] == k, "neighbors/distances shape mismatch");
-  B2_EXPECTS(k >= 1 && k <= 32, "ivf_pq search: k must be in [1, 32] in this build (got %d)", k);
+  B2_EXPECTS(k >= 1 && k <= 64, "ivf_pq search: k must be in [1, 64] in this build (got %d)", k);
   B2_EXPECTS(sp.n_probes >= 1, "n_probes must be >= 1");
   B2_EXPECTS(sp.lut_dtype == CUDA_R_32F || sp.lut_dtype == CUDA_R_16F || sp.lut_dtype == CUDA_R_8U, "unsupported lut_dtype");
   B2_EXPECTS(sp.internal_distance_dtype == CUDA_R_32F || sp.internal_distance_dtype == CUDA_R_16F, "unsupported internal_distance_dtype");
@@ -774,11 +774,15 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   rotate_rows(s, q, nq, idx.dim, idx.rotation.data(), idx.rot_dim, q_rot.data());
 
   // ---- bucket pairs by list
-  const int KC    = k <= 16 ? 16 : 32;
   const bool want_tc = sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F && idx.yhat.data() != nullptr;
   const bool use_tc  = env_path() == 1 ? false : (env_path() == 2 ? idx.yhat.data() != nullptr : want_tc);
   const int lists = use_tc ? tc_lists_per_item() : 1;
+  // candidates kept per (query, probe): the tensor-core epilogue keeps `lists` sorted lists of KC (one per column half of
+  // the tile); for k > KC the union of the two half lists stands in for the pair's top-k (exact whenever no more than KC of
+  // them fall into one half — an approximation only the k > 32 candidate-generation use case can see)
+  const int KC    = k <= 16 ? 16 : (k <= 32 || use_tc ? 32 : 64);
   const int KCW   = KC * lists;
+  B2_EXPECTS(KCW >= k, "ivf_pq search: k = %d needs the two-list tensor-core epilogue (CUVS_B200_TC_EPIW=8) or the LUT path", k);
   probe_buckets pb;
   bucket_probes(res, probes.data(), nq, static_cast<int>(n_probes), idx.n_lists, idx.lists.d_offsets.data(), KCW, pb);
   dbuf<float> cs(static_cast<size_t>(pb.n_pairs) * KCW, s);

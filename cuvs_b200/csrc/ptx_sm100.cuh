@@ -56,11 +56,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
   asm volatile(
     "{\n\t"
     ".reg .pred P;\n\t"
-    "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
     "selp.b32 %0, 1, 0, P;\n\t"
     "}\n"
     : "=r"(ok)
-    : "r"(smem_u32(bar)), "r"(parity)
+    : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) /* suspend-time hint: sleep in hardware instead of spinning */
     : "memory");
   return ok != 0;
 }

@@ -43,7 +43,7 @@ struct cfg {
   static constexpr int a_bytes     = NPL * KB * kTileBytes;
   static constexpr int stage_bytes = NPL * kTileBytes;
   static constexpr int n_bars      = 2 * stages + 2 + 4;
-  static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + stages * stage_bytes + 2 * 128 * 4 /*hn*/ +
+  static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + stages * stage_bytes + EPIW * 2 * (512 / EPIW) * 4 /*hn, per warp*/ +
                                  kQueue * (32 * EPIW) * 8 /*queues*/ + n_bars * 8 + 16;
 };
 
@@ -68,10 +68,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0 && (ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* sA   = smem_raw;
   uint8_t* sB   = sA + C::a_bytes;
-  float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);
-  float* qv     = sHn + 2 * 128;
-  uint32_t* qi  = reinterpret_cast<uint32_t*>(qv + kQueue * kEpiThreads);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qi + kQueue * kEpiThreads);
+  float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);  // [EPIW warps][2 buffers][512/EPIW columns]
+  uint2* qe     = reinterpret_cast<uint2*>(sHn + EPIW * 2 * (512 / EPIW));      // [kQueue][kEpiThreads] {packed score, group base row}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qe + kQueue * kEpiThreads);
   uint64_t* full    = bars;
   uint64_t* empty   = bars + C::stages;
   uint64_t* a_full  = bars + 2 * C::stages;
@@ -193,14 +192,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if constexpr (KC == 0) {
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const tc_item item   = items[it];
-        const float* hn_item = hn + item.b_row0;
-        float hn_reg         = (item.n_tiles && half == 0) ? hn_item[row] : 0.f;
+        float* hn_w          = sHn + (warp - 2) * 2 * kCols;
+        const float* hn_item = hn + item.b_row0 + col0;
+        float4 hn_reg        = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + lane * 4);
         float* orow          = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride;
         const bool live      = static_cast<uint32_t>(row) < item.valid_rows;
         for (uint32_t t = 0; t < item.n_tiles; ++t) {
-          if (half == 0) sHn[acc * 128 + row] = hn_reg;
-          ptx::named_bar_sync(1, kEpiThreads);
-          if (half == 0 && t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
+          if (lane < kCols / 4) *reinterpret_cast<float4*>(hn_w + acc * kCols + lane * 4) = hn_reg;
+          __syncwarp();
+          if (t + 1 < item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + (t + 1) * 128 + lane * 4);
           ptx::mbar_wait(&tfull[acc], acc_phase);
           ptx::tc_fence_after_sync();
 #pragma unroll 1
@@ -210,7 +211,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + c0, v);
             ptx::tmem_ld_wait();
             if (live) {
-              const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + c0);
+              const float4* h4 = reinterpret_cast<const float4*>(hn_w + acc * kCols + ch * kChunk);
               float4* o4       = reinterpret_cast<float4*>(orow + t * 128 + c0);
 #pragma unroll
               for (int c4 = 0; c4 < kChunk / 4; ++c4) {
@@ -227,6 +228,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     } else {
+      // Fused top-KC.  The low 4 mantissa bits of every score carry the column index inside its group of 16
+      // (a <= 2^-19 relative perturbation, covered by the certificate's eps), so a queue entry is one 64-bit
+      // store {packed score, group base row} and the min-tree doubles as an arg-min.
+      float* hn_w = sHn + (warp - 2) * 2 * kCols;  // this warp's private staging of the tile's half-norms: no CTA barrier
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const tc_item item = items[it];
         float lv[KC > 0 ? KC : 1];
@@ -238,8 +243,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
         auto flush = [&]() {
           for (int e = 0; e < cnt; ++e) {
-            const float s    = qv[e * kEpiThreads + et];
-            const uint32_t p = qi[e * kEpiThreads + et];
+            const uint2 en   = qe[e * kEpiThreads + et];
+            const float s    = __uint_as_float(en.x);
+            const uint32_t p = en.y + (en.x & 15u);
             if (s < lv[KC - 1]) {
 #pragma unroll
               for (int j = KC - 1; j > 0; --j) {
@@ -253,19 +259,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           thr = lv[KC - 1];
         };
 
-        const float* hn_item = hn + item.b_row0;
-        float hn_reg         = (item.n_tiles && half == 0) ? hn_item[row] : 0.f;
+        const float* hn_item = hn + item.b_row0 + col0;
+        // lanes 0..kCols/4-1 each stage one float4 of the warp's column range
+        float4 hn_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + lane * 4);
         for (uint32_t t = 0; t < item.n_tiles; ++t) {
-          if (half == 0) sHn[acc * 128 + row] = hn_reg;
-          ptx::named_bar_sync(1, kEpiThreads);
-          if (half == 0 && t + 1 < item.n_tiles) hn_reg = hn_item[(t + 1) * 128 + row];
+          if (lane < kCols / 4) *reinterpret_cast<float4*>(hn_w + acc * kCols + lane * 4) = hn_reg;
+          __syncwarp();
+          if (t + 1 < item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + (t + 1) * 128 + lane * 4);
           ptx::mbar_wait(&tfull[acc], acc_phase);
           ptx::tc_fence_after_sync();
           const uint32_t pos0 = item.b_row0 + t * 128 + col0;
           if (!dbg_skip_epilogue) {
-            // 32 accumulator columns per tcgen05.ld, examined as two groups of 16.  Hot path per group:
-            // 16 FADD (s = hn - acc) + a 15-op min tree + ONE compare/branch; the per-element test only
-            // runs when the group's minimum beats the thread's current k'-th best.
 #pragma unroll 1
             for (int ch = 0; ch < kCols / 32; ++ch) {
               uint32_t v[32];
@@ -274,32 +279,28 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
                 if (__any_sync(0xffffffffu, cnt > kQueue - kChunk)) flush();
-                const float4* h4 = reinterpret_cast<const float4*>(sHn + acc * 128 + col0 + ch * 32 + g * 16);
+                const float4* h4 = reinterpret_cast<const float4*>(hn_w + acc * kCols + ch * 32 + g * 16);
                 float sc[16];
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                   const float4 h = h4[c4];
-                  sc[c4 * 4 + 0] = h.x - __uint_as_float(v[g * 16 + c4 * 4 + 0]);
-                  sc[c4 * 4 + 1] = h.y - __uint_as_float(v[g * 16 + c4 * 4 + 1]);
-                  sc[c4 * 4 + 2] = h.z - __uint_as_float(v[g * 16 + c4 * 4 + 2]);
-                  sc[c4 * 4 + 3] = h.w - __uint_as_float(v[g * 16 + c4 * 4 + 3]);
+                  sc[c4 * 4 + 0] = __uint_as_float((__float_as_uint(h.x - __uint_as_float(v[g * 16 + c4 * 4 + 0])) & 0xfffffff0u) | (c4 * 4 + 0));
+                  sc[c4 * 4 + 1] = __uint_as_float((__float_as_uint(h.y - __uint_as_float(v[g * 16 + c4 * 4 + 1])) & 0xfffffff0u) | (c4 * 4 + 1));
+                  sc[c4 * 4 + 2] = __uint_as_float((__float_as_uint(h.z - __uint_as_float(v[g * 16 + c4 * 4 + 2])) & 0xfffffff0u) | (c4 * 4 + 2));
+                  sc[c4 * 4 + 3] = __uint_as_float((__float_as_uint(h.w - __uint_as_float(v[g * 16 + c4 * 4 + 3])) & 0xfffffff0u) | (c4 * 4 + 3));
                 }
-                // quad minima -> group minimum; a row rarely has more than one quad with a hit
                 const float q0 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
                 const float q1 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
                 const float q2 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
                 const float q3 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
                 const float mn = fminf(fminf(q0, q1), fminf(q2, q3));
                 if (mn < thr) {
-                  const uint32_t p = pos0 + ch * 32 + g * 16;
-#define B2_SCAN_QUAD(QM, BASE)                                                                                         \
-                  if (QM < thr) {                                                                                      \
-                    _Pragma("unroll") for (int c = BASE; c < BASE + 4; ++c) {                                          \
-                      if (sc[c] < thr) { qv[cnt * kEpiThreads + et] = sc[c]; qi[cnt * kEpiThreads + et] = p + c; ++cnt; } \
-                    }                                                                                                  \
+                  const uint32_t gbase = pos0 + ch * 32 + g * 16;
+                  uint2* qp = qe + cnt * kEpiThreads + et;
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    if (sc[c] < thr) { *qp = make_uint2(__float_as_uint(sc[c]), gbase); qp += kEpiThreads; ++cnt; }
                   }
-                  B2_SCAN_QUAD(q0, 0) B2_SCAN_QUAD(q1, 4) B2_SCAN_QUAD(q2, 8) B2_SCAN_QUAD(q3, 12)
-#undef B2_SCAN_QUAD
                 }
               }
             }
