@@ -415,6 +415,20 @@ cuvsError_t cuvsB200IvfFlatGetListIndices(cuvsIvfFlatIndex_t index, uint32_t lab
     dl_fill_view(ids, idx.ids.data() + idx.lists.h_offsets[label], idx.device, DLDataType{kDLInt, 64, 1}, 1, shape);
   });
 }
+cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFlatIndex_t index, DLManagedTensor* centers)
+{
+  return guarded([=] {
+    auto r    = as_res(res);
+    auto& idx = flat_of(index);
+    B2_EXPECTS(centers != nullptr, "centers is null");
+    const DLTensor& c = centers->dl_tensor;
+    B2_EXPECTS(dl_is(c, kDLFloat, 32) && c.ndim == 2 && c.shape[0] == idx.n_lists && c.shape[1] == idx.dim && dl_is_c_contiguous(c),
+               "centers must be float32 [n_lists, dim]");
+    B2_EXPECTS(idx.lists.size == 0, "centres can only be replaced while the index is empty");
+    B2_CUDA(cudaMemcpyAsync(idx.centers.data(), dl_ptr<float>(c), sizeof(float) * idx.n_lists * idx.dim, cudaMemcpyDefault, r->stream));
+    refresh_centers_tc(r, idx);
+  });
+}
 cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t* size) { return guarded([=] { *size = flat_of(index).lists.size; }); }
 
 cuvsError_t cuvsIvfFlatBuild(cuvsResources_t res, cuvsIvfFlatIndexParams_t params, DLManagedTensor* dataset, cuvsIvfFlatIndex_t index)

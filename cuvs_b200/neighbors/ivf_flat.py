@@ -156,3 +156,10 @@ def load(filename, resources=None):
     check(lib.cuvsIvfFlatDeserialize(resources.get_c_obj(), str(filename).encode(), idx._p))
     idx.trained = True
     return idx
+
+
+@auto_sync_resources
+def set_centers(index, centers, resources=None):
+    """cuvsB200IvfFlatSetCenters (extension): overwrite the coarse centres of an empty index."""
+    check(lib.cuvsB200IvfFlatSetCenters(resources.get_c_obj(), index._p, DL(as_tensor(centers)).ptr))
+    return index

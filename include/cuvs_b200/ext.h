@@ -37,6 +37,9 @@ CUVS_EXPORT cuvsError_t cuvsB200BruteForceCandidates(cuvsResources_t res,
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetListSizes(cuvsIvfFlatIndex_t index, DLManagedTensor* list_sizes /*[n_lists] u32*/);
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetListIndices(cuvsIvfFlatIndex_t index, uint32_t label, DLManagedTensor* ids /*[size] i64*/);
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t* size);
+/* Replace the coarse centres of an (empty) index — used by the list-sharded multi-GPU build so that every rank
+ * partitions the data with bit-identical centres (trained on one rank, broadcast over NCCL). centers: [n_lists, dim] f32. */
+CUVS_EXPORT cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFlatIndex_t index, DLManagedTensor* centers);
 
 #ifdef __cplusplus
 }
