@@ -1,0 +1,120 @@
+"""CPU: the C-ABI library loads and exports every symbol the headers under include/ declare; struct layouts used by the
+Python binding match the C definitions (sizes probed by compiling a tiny C program against the headers); error paths
+return CUVS_ERROR with text and never throw.  No GPU compute calls."""
+import ctypes as C
+import glob
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+
+
+def _declared_symbols():
+    syms = set()
+    for h in glob.glob(os.path.join(INC, "**", "*.h"), recursive=True):
+        txt = open(h).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"CUVS_EXPORT\s+[\w\s\*]+?\b(cuvs\w+)\s*\(", txt):
+            syms.add(m.group(1))
+    return sorted(syms)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cuvs_b200 import build
+    path = build.build()
+    return C.CDLL(path)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) > 100
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/ but not exported: {missing}"
+
+
+def test_headers_compile_as_plain_c_and_struct_sizes_match_binding():
+    """c/tests/core/headers.c analogue: the headers are pure C; and the ctypes mirrors have the compiler's sizes."""
+    src = r'''
+#include <stdio.h>
+#include <cuvs/core/all.h>
+#include <cuvs_b200/ext.h>
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(struct cuvsIvfFlatIndexParams), sizeof(struct cuvsIvfPqIndexParams),
+         sizeof(struct cuvsIvfPqSearchParams), sizeof(struct cuvsCagraIndexParams), sizeof(struct cuvsCagraSearchParams),
+         sizeof(struct cuvsKMeansParams), sizeof(DLManagedTensor), sizeof(cuvsBruteForceIndex), sizeof(cuvsFilter));
+  return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "h.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "h")
+        subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", INC, "-I", "/usr/local/cuda/include", c, "-o", exe], check=True)
+        sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    from cuvs_b200 import _capi
+    from cuvs_b200.cluster import kmeans
+    from cuvs_b200.neighbors import cagra, ivf_flat, ivf_pq
+    ours = [C.sizeof(ivf_flat._IndexParamsC), C.sizeof(ivf_pq._IndexParamsC), C.sizeof(ivf_pq._SearchParamsC), C.sizeof(cagra._IndexParamsC),
+            C.sizeof(cagra._SearchParamsC), C.sizeof(kmeans._ParamsC), C.sizeof(_capi.DLManagedTensor), C.sizeof(_capi.index_handle),
+            C.sizeof(_capi.cuvsFilter)]
+    assert ours == sizes
+
+
+def test_param_defaults_match_reference(lib):
+    """c/src/neighbors/{ivf_flat,ivf_pq,cagra}.cpp ParamsCreate defaults."""
+    from cuvs_b200.neighbors import cagra, ivf_flat, ivf_pq
+    p = C.POINTER(ivf_flat._IndexParamsC)()
+    assert lib.cuvsIvfFlatIndexParamsCreate(C.byref(p)) == 1
+    c = p.contents
+    assert (c.metric, c.metric_arg, c.add_data_on_build, c.n_lists, c.kmeans_n_iters, c.kmeans_trainset_fraction) == (0, 2.0, True, 1024, 20, 0.5)
+    lib.cuvsIvfFlatIndexParamsDestroy(p)
+    p = C.POINTER(ivf_pq._IndexParamsC)()
+    assert lib.cuvsIvfPqIndexParamsCreate(C.byref(p)) == 1
+    c = p.contents
+    assert (c.pq_bits, c.pq_dim, c.codebook_kind, c.max_train_points_per_pq_code, c.codes_layout) == (8, 0, 0, 256, 1)
+    lib.cuvsIvfPqIndexParamsDestroy(p)
+    p = C.POINTER(ivf_pq._SearchParamsC)()
+    assert lib.cuvsIvfPqSearchParamsCreate(C.byref(p)) == 1
+    c = p.contents
+    assert (c.n_probes, c.lut_dtype, c.internal_distance_dtype, c.max_internal_batch_size, c.preferred_shmem_carveout) == (20, 0, 0, 4096, 1.0)
+    lib.cuvsIvfPqSearchParamsDestroy(p)
+    p = C.POINTER(cagra._SearchParamsC)()
+    assert lib.cuvsCagraSearchParamsCreate(C.byref(p)) == 1
+    c = p.contents
+    assert (c.itopk_size, c.search_width, c.num_random_samplings, c.rand_xor_mask) == (64, 1, 1, 0x128394)
+    assert abs(c.hashmap_max_fill_rate - 0.5) < 1e-7
+    lib.cuvsCagraSearchParamsDestroy(p)
+
+
+def test_errors_are_codes_with_text_not_exceptions(lib):
+    lib.cuvsGetLastErrorText.restype = C.c_char_p
+    h = C.c_size_t(0)
+    rc = lib.cuvsResourcesCreate(C.byref(h))  # no GPU in this container -> CUVS_ERROR + message
+    if rc == 0:
+        assert b"CUDA" in lib.cuvsGetLastErrorText()
+    lib.cuvsSetLastErrorText(None)
+    assert lib.cuvsGetLastErrorText() is None
+    lib.cuvsSetLastErrorText(b"boom")
+    assert lib.cuvsGetLastErrorText() == b"boom"
+    major, minor, patch = C.c_uint16(), C.c_uint16(), C.c_uint16()
+    assert lib.cuvsVersionGet(C.byref(major), C.byref(minor), C.byref(patch)) == 1 and (major.value, minor.value) == (26, 8)
+    lib.cuvsSetLogLevel(4)
+    assert lib.cuvsGetLogLevel() == 4
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under cuvs_b200/ may reference it."""
+    bad = []
+    for f in glob.glob(os.path.join(ROOT, "cuvs_b200", "**", "*"), recursive=True):
+        if os.path.isfile(f) and f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp")):
+            txt = open(f, errors="ignore").read()
+            if re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M) or "liboracle" in txt:
+                bad.append(f)
+    assert not bad, bad
