@@ -257,8 +257,13 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
   const int64_t row_stride = static_cast<int64_t>(splits) * KCW;
   dbuf<float> cs(static_cast<size_t>(nq_pad) * row_stride, stream);
   dbuf<uint32_t> cp(static_cast<size_t>(nq_pad) * row_stride, stream);
+  // the splits of one query row share a running k'-th-best bound (scores are comparable: same query)
+  dbuf<int> bkeys(static_cast<size_t>(nq_pad), stream);
+  B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq_pad, stream));
+  tc_bound bnd;
+  bnd.keys = bkeys.data();
   tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
-               idx.hn.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride);
+               idx.hn.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd);
   if (row_stride > KC) {
     out.score.alloc(static_cast<size_t>(nq) * KC, stream);
     out.pos.alloc(static_cast<size_t>(nq) * KC, stream);

@@ -175,10 +175,12 @@ __device__ __forceinline__ float team_distance(const float* __restrict__ row, co
 }
 
 // EI = itopk / 32, EC = (search_width * degree rounded up to 32) / 32 ; buffer = EI + EC keys per lane
+constexpr int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
 template <int EI, int EC>
 __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
 {
-  constexpr int EB = EI + EC;
+  constexpr int EB = next_pow2(EI + EC);  // the bitonic network needs a power-of-two key count; spare keys stay ~0 (sort last)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = static_cast<int64_t>(blockIdx.x) * warps + wid;
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
     __syncwarp();
     // ---- candidates -> register keys EI..EB-1
 #pragma unroll
-    for (int e = 0; e < EC; ++e) {
+    for (int e = 0; e < EB - EI; ++e) {
       const int c = e * 32 + lane;
-      key[EI + e] = c < n_new ? (static_cast<uint64_t>(dist_key(sdist[c])) << 32) | scand[c] : ~0ull;
+      key[EI + e] = (e < EC && c < n_new) ? (static_cast<uint64_t>(dist_key(sdist[c])) << 32) | scand[c] : ~0ull;
     }
     __syncwarp();
     ++iter;
@@ -422,8 +424,10 @@ void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchP
     p.hash_global = gh.data();
   }
   const int qpad = (idx.dim + 3) & ~3;
+  int ebp = 1;
+  while (ebp < EI + EC) ebp <<= 1;
   const size_t per_warp = static_cast<size_t>(qpad) * 4 + (pl.small_hash_bitlen ? (size_t(4) << pl.small_hash_bitlen) : 0) +
-                          static_cast<size_t>(EI + EC) * 32 * 8 + 16;
+                          static_cast<size_t>(ebp) * 32 * 8 + 16;
 #define B2_CAGRA_CASE(EI_, EC_) if (EI == EI_ && EC == EC_) { launch_search<EI_, EC_>(s, p, per_warp); launched = true; }
   bool launched = false;
   B2_CAGRA_CASE(1, 1) B2_CAGRA_CASE(1, 2) B2_CAGRA_CASE(1, 4)

@@ -314,9 +314,15 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   dbuf<float> cs(static_cast<size_t>(pb.n_pairs) * KCW, s);
   dbuf<uint32_t> cp(static_cast<size_t>(pb.n_pairs) * KCW, s);
   {
+    // probes of one query share a running k'-th-best bound (same query => comparable scores)
+    dbuf<int> bkeys(static_cast<size_t>(nq), s);
+    B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq, s));
+    tc_bound bnd;
+    bnd.keys = bkeys.data();
+    bnd.idx  = pb.pair_query.data();
     timed_section ts("ivf_flat_scan", s);
     tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.hi.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                 idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW);
+                 idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
   }
 
   // ---- 4. per query: merge probes by approximate score, exact re-score, ids

@@ -800,12 +800,20 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
                                                                    pb.pair_list.data(), pb.n_items.data() + 1, a_rows, idx.rot_dim, idx.Kp, ip,
                                                                    a_hi.data(), nullptr, add.data());
     B2_CUDA(cudaGetLastError());
+    scale = ip ? 1.0f : 2.0f;  // L2: |r|^2 + 2 (|y|^2/2 - r.y); IP: -(q.(c+y))
     {
+      // probes of one query share a running bound on its k'-th best DISTANCE: d = add[slot] + scale * s
+      dbuf<int> bkeys(static_cast<size_t>(nq), s);
+      B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq, s));
+      tc_bound bnd;
+      bnd.keys  = bkeys.data();
+      bnd.idx   = pb.pair_query.data();
+      bnd.add   = add.data();
+      bnd.scale = scale;
       timed_section ts("pq_scan", s);
       tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                   idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW);
+                   idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
     }
-    scale = ip ? 1.0f : 2.0f;  // L2: |r|^2 + 2 (|y|^2/2 - r.y); IP: -(q.(c+y))
   } else {
     const int book      = idx.book();
     const size_t lut_b  = sp.lut_dtype == CUDA_R_32F ? 4 : (sp.lut_dtype == CUDA_R_16F ? 2 : 1);

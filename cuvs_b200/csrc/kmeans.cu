@@ -45,6 +45,66 @@ __global__ void weighted_cost_kernel(const float* __restrict__ s, const float* _
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// ---- k-means++ seeding (D^2 sampling, one centre per step).  Sampling proportional to w_i is done as
+// argmax_i w_i / E_i with E_i ~ Exp(1) drawn from a counter-based hash, so a step is one pass + one 64-bit atomicMax.
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void kpp_step_kernel(const float* __restrict__ x, int64_t n, int d, int64_t new_row, float* __restrict__ mind, int step,
+                                unsigned long long* __restrict__ best)
+{
+  extern __shared__ float c[];
+  for (int j = threadIdx.x; j < d; j += blockDim.x) c[j] = x[new_row * d + j];
+  __syncthreads();
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  unsigned long long key = 0;
+  if (i < n) {
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) { float t = x[i * d + j] - c[j]; acc = fmaf(t, t, acc); }
+    float m = step == 0 ? acc : fminf(mind[i], acc);
+    mind[i] = m;
+    const uint64_t h = mix64((static_cast<uint64_t>(step) << 40) ^ static_cast<uint64_t>(i));
+    const float u    = (static_cast<float>(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    const float e    = -__logf(u);
+    const float w    = m / fmaxf(e, 1e-20f);
+    key = (static_cast<unsigned long long>(__float_as_uint(w)) << 32) | static_cast<uint32_t>(i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+    key = t > key ? t : key;
+  }
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
+}
+__global__ void copy_row_kernel(const float* __restrict__ x, int64_t row, int d, float* __restrict__ dst)
+{
+  for (int j = threadIdx.x; j < d; j += blockDim.x) dst[j] = x[row * d + j];
+}
+
+void kmeanspp_init(resources* r, const float* x, int64_t n, int d, int k, float* centers)
+{
+  auto s = r->stream;
+  dbuf<float> mind(static_cast<size_t>(n), s);
+  dbuf<unsigned long long> best(1, s);
+  int64_t row = static_cast<int64_t>(0x2545F4914F6CDD1DULL % static_cast<uint64_t>(n));  // fixed first pick (rng_state{0} analogue)
+  for (int c = 0; c < k; ++c) {
+    copy_row_kernel<<<1, 128, 0, s>>>(x, row, d, centers + static_cast<int64_t>(c) * d);
+    if (c + 1 == k) break;
+    B2_CUDA(cudaMemsetAsync(best.data(), 0, sizeof(unsigned long long), s));
+    count_launch(2);
+    kpp_step_kernel<<<blocks_for(n, 256), 256, d * sizeof(float), s>>>(x, n, d, row, mind.data(), c, best.data());
+    unsigned long long h = 0;
+    B2_CUDA(cudaMemcpyAsync(&h, best.data(), sizeof(h), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    row = static_cast<int64_t>(h & 0xffffffffull);
+  }
+  B2_CUDA(cudaGetLastError());
+}
+
 struct dev_matrix {
   const float* p = nullptr;
   dbuf<float> staged;
@@ -117,9 +177,13 @@ void fit(resources* r, const fit_args& a, DLManagedTensor* X, DLManagedTensor* s
   int iters = 0;
   double cost = 0;
   const int max_iter = a.balanced ? std::max(a.balanced_iters, 1) : std::max(a.max_iter, 1);
-  // KMeansPlusPlus / Random both start from evenly strided rows here (kmeans.cuh:789-978 draws k-means|| seeds; the Lloyd
-  // refinement below is what the hot path covers)
-  kmeans_train(r, x.p, x.n, x.d, a.n_clusters, max_iter, c, a.init != Array, a.balanced, &cost, &iters, a.balanced ? 0.0 : a.tol);
+  // KMeansPlusPlus: D^2 seeding (one pass per centre) up to 4096 clusters, evenly strided rows beyond / for Random
+  bool strided = a.init != Array;
+  if (a.init == KMeansPlusPlus && a.n_clusters <= 4096 && x.n < (int64_t(1) << 32)) {
+    kmeanspp_init(r, x.p, x.n, x.d, a.n_clusters, c);
+    strided = false;
+  }
+  kmeans_train(r, x.p, x.n, x.d, a.n_clusters, max_iter, c, strided, a.balanced, &cost, &iters, a.balanced ? 0.0 : a.tol);
   if (inertia) *inertia = cost;
   if (n_iter) *n_iter = iters;
 }

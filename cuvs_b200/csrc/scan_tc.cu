@@ -57,7 +57,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const float* __restrict__ hn, const tc_item* __restrict__ items, int n_items_host,
                const int* __restrict__ n_items_dev, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
-               int64_t out_row_stride, int dbg_skip_epilogue)
+               int64_t out_row_stride, int dbg_skip_epilogue, tc_bound bound)
 {
   using C = cfg<KB, NPL, EPIW>;
   constexpr int kEpiThreads = 32 * EPIW;
@@ -238,7 +238,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t li[KC > 0 ? KC : 1];
 #pragma unroll
         for (int j = 0; j < KC; ++j) { lv[j] = INFINITY; li[j] = 0xffffffffu; }
-        float thr = INFINITY;
+        // cross-item pruning bound of this row's query (see tc_bound)
+        float thr0 = INFINITY, b_add = 0.f;
+        int* b_key = nullptr;
+        if (bound.keys != nullptr && static_cast<uint32_t>(row) < item.valid_rows) {
+          const uint32_t arow = item.a_row0 + row;
+          b_key               = bound.keys + (bound.idx ? bound.idx[arow] : arow);
+          b_add               = bound.add ? bound.add[arow] : 0.f;
+          const int kb        = *reinterpret_cast<volatile int*>(b_key);
+          const float bv      = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
+          thr0                = (bv - b_add) / bound.scale;
+        }
+        float thr = thr0;
         int cnt   = 0;
 
         auto flush = [&]() {
@@ -256,7 +267,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           cnt = 0;
-          thr = lv[KC - 1];
+          thr = fminf(thr0, lv[KC - 1]);
         };
 
         const float* hn_item = hn + item.b_row0 + col0;
@@ -311,6 +322,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (acc == 0) acc_phase ^= 1;
         }
         flush();
+        if (b_key != nullptr && lv[KC - 1] < INFINITY) {
+          const float pub = b_add + bound.scale * lv[KC - 1];
+          const int kp    = __float_as_int(pub);
+          atomicMin(b_key, kp >= 0 ? kp : kp ^ 0x7fffffff);
+        }
         if (static_cast<uint32_t>(row) < item.valid_rows) {
           float* os    = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
           uint32_t* op = out_pos + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
@@ -369,7 +385,7 @@ int env_int(const char* name, int dflt)
 template <int KB, int NPL, int KC, int EPIW>
 void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
             const CUtensorMap& b_lo, const float* hn, const tc_item* items, int n_items, const int* n_items_dev,
-            float* out_score, uint32_t* out_pos, int64_t out_row_stride)
+            float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound)
 {
   auto kern = tc_scan_kernel<KB, NPL, KC, EPIW>;
   using C   = cfg<KB, NPL, EPIW>;
@@ -383,7 +399,7 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
   timed_section ts("tc_scan", stream);
   count_launch();
   kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, n_items_dev, out_score, out_pos,
-                                               out_row_stride, skip_epi);
+                                               out_row_stride, skip_epi, bound);
   B2_CUDA(cudaGetLastError());
 }
 
@@ -456,7 +472,7 @@ void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
                   const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
-                  float* out_score, uint32_t* out_pos, int64_t out_row_stride)
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound)
 {
   if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
   B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
@@ -465,6 +481,8 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   B2_EXPECTS(passes == 1 || (a_lo && b_lo), "tc_scan_topk: lo planes required for 3-pass mode");
   const int sms  = sm_count_of(device);
   const int epiw = tc_lists_per_item() * 4;
+  static const int no_bound = env_int("CUVS_B200_TC_NO_BOUND", 0);  // profiling knob
+  const tc_bound bnd = (bound && !no_bound) ? *bound : tc_bound{};
   CUtensorMap mA  = make_plane_map(a_hi, a_rows_pad, Kp);
   CUtensorMap mB  = make_plane_map(b_hi, b_rows_pad, Kp);
   CUtensorMap mAl = passes == 3 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
@@ -473,8 +491,8 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
   {                                                                                                                    \
     if (epiw == 8)                                                                                                     \
-      return launch<KB_, NPL_, KC_, 8>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride); \
-    return launch<KB_, NPL_, KC_, 4>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride);   \
+      return launch<KB_, NPL_, KC_, 8>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd); \
+    return launch<KB_, NPL_, KC_, 4>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd);   \
   }
   B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 2, 0)
   B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 2, 0)

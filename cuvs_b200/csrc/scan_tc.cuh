@@ -23,6 +23,23 @@ struct tc_item {
   uint64_t out_off;     // element offset of (row 0, slot 0) in out_score/out_pos
 };
 
+/**
+ * Optional cross-item pruning bound (the role of `query_kths` in the reference's compute_similarity kernel,
+ * cpp/src/neighbors/ivf_pq/detail/jit_lto_kernels/compute_distances_impl.cuh:64-65,96): work items that scan different
+ * row ranges for the SAME query share one running upper bound on that query's k'-th best value.  An item starts with
+ *   thr = (bound[b] - add[a_row]) / scale      b = idx ? idx[a_row] : a_row
+ * instead of +inf and publishes  add[a_row] + scale * (its k'-th best score)  with an atomic min when its list is full.
+ * Values are stored as order-preserving ints (tc_bound_init_value = "+inf").  Rows dropped by the bound can never be
+ * among the query's k' best, so results (and the brute-force certificate) are unchanged.
+ */
+struct tc_bound {
+  int* keys           = nullptr;  // [n_bounds] ordered-int encoded floats
+  const uint32_t* idx = nullptr;  // [a_rows] bound slot of every A row (null: the A row itself)
+  const float* add    = nullptr;  // [a_rows] (null: 0)
+  float scale         = 1.0f;
+};
+constexpr int tc_bound_init_byte = 0x7f;  // memset value: 0x7f7f7f7f decodes to 3.39e38
+
 inline int tc_pad_k(int d) { return (d + 63) / 64 * 64; }
 inline int64_t tc_pad_rows(int64_t n) { return (n + kTcTile - 1) / kTcTile * kTcTile; }
 
@@ -55,6 +72,6 @@ void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
                   const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
-                  float* out_score, uint32_t* out_pos, int64_t out_row_stride);
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound = nullptr);
 
 }  // namespace b200

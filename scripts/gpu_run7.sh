@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== tests" > gpurun_out/r7_tests.log
+timeout 1800 python -m pytest tests -m gpu -q --timeout=900 >> gpurun_out/r7_tests.log 2>&1
+echo "== brute (bound)" > gpurun_out/r7_bench.log
+timeout 600 python bench.py --workload brute_force --steps 5 --warmup 3 --no-cpu >> gpurun_out/r7_bench.log 2>&1
+echo "== brute (no bound)" >> gpurun_out/r7_bench.log
+CUVS_B200_TC_NO_BOUND=1 timeout 600 python bench.py --workload brute_force --steps 5 --warmup 3 --no-cpu >> gpurun_out/r7_bench.log 2>&1
+echo "== ivf_pq (bound)" >> gpurun_out/r7_bench.log
+timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu >> gpurun_out/r7_bench.log 2>&1
+echo "== ivf_pq (no bound)" >> gpurun_out/r7_bench.log
+CUVS_B200_TC_NO_BOUND=1 timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu >> gpurun_out/r7_bench.log 2>&1
+tail -n 30 gpurun_out/r7_tests.log | cut -c1-300
+python - <<'PY'
+import json
+for line in open('gpurun_out/r7_bench.log'):
+    line=line.strip()
+    if line.startswith('=='): print(line); continue
+    if line.startswith('{'):
+        j=json.loads(line)
+        print(' value %.0f e2e %.0f ms/step %.3f kernel_ms %.3f frac %.3f parity %s recall %s' % (j['value'], j['e2e']['value'], j['ms_per_step'], j['roofline']['kernel_ms'], j['roofline']['frac'], j['parity_spot_check'], j['config'].get('recall_at_10')))
+    elif 'Error' in line: print('  ', line[:300])
+PY
