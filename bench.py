@@ -343,7 +343,85 @@ class IvfPqWorkload:
                           "reference has no CPU IVF-PQ search"}
 
 
-WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload}
+class CagraWorkload:
+    """configs[3]: cagra::search 10M x 96 f32, graph_degree=64 itopk=64, batch 10k."""
+    dtype = "f32"
+    timing_section = "cagra_search"
+
+    def __init__(self, n=10_000_000, d=96, nq=10_000, k=10, degree=64, itopk=64, seed=1234, rank=0, world=1):
+        from cuvs_b200.neighbors import brute_force, cagra
+        self.n, self.d, self.nq, self.k, self.degree, self.itopk = n, d, nq, k, degree, itopk
+        self.name = f"cagra {n // 1_000_000}M x {d} f32, graph_degree={degree} itopk={itopk} search_width=1, batch {nq}, k={k}"
+        self.cagra = cagra
+        self.dataset = gen_manifold(n, d, seed)
+        self.queries = gen_manifold(nq, d, seed + 3087)
+        t0 = time.time()
+        self.index = cagra.build(cagra.IndexParams(graph_degree=degree, intermediate_graph_degree=2 * degree), self.dataset)
+        torch.cuda.synchronize()
+        self.build_s = time.time() - t0
+        self.sp = cagra.SearchParams(itopk_size=itopk)
+        self.h_queries = self.queries.cpu().pin_memory()
+        self.neighbors = torch.empty((nq, k), dtype=torch.uint32, device="cuda")
+        self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        self.h_neighbors = torch.empty((nq, k), dtype=torch.uint32).pin_memory()
+        self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        bf = brute_force.build(self.dataset)
+        _, self.gt = brute_force.search(bf, self.queries, k)
+        del bf
+        self.recall = None
+
+    def step(self, res):
+        self.cagra.search(self.sp, self.index, self.queries, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+
+    def e2e_step(self, res):
+        q = self.h_queries.to("cuda", non_blocking=True)
+        self.cagra.search(self.sp, self.index, q, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+        self.h_neighbors.copy_(self.neighbors, non_blocking=True)
+        self.h_distances.copy_(self.distances, non_blocking=True)
+
+    def e2e_bytes(self):
+        return self.nq * self.d * 4, self.nq * self.k * 8
+
+    def units(self):
+        return self.nq
+
+    def check(self):
+        nb = self.neighbors.to(torch.int64)
+        self.recall = (nb.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
+        return self.recall >= 0.95
+
+    def config(self):
+        return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
+                "graph_degree": self.degree, "itopk": self.itopk, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "data": "rank-16 gaussian manifold in 96-d + 0.05 noise (embedding-like), seeds 1234/4321",
+                "l2_flush": "256 MiB write between timed steps", "parallelism": "single GPU"}
+
+    def roofline(self, kernel_ms, pk):
+        # upper bound of the walk's traffic (SURVEY 8d): (itopk + iters*degree) vector rows + iters adjacency rows per query
+        iters = self.itopk + 5
+        bytes_ub = self.nq * ((self.itopk + self.degree + iters * self.degree) * self.d * 4 + iters * self.degree * 4)
+        ach = bytes_ub / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "cagra_search_kernel (one warp per query, register bitonic top-k, smem hash)", "achieved": ach,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "peak_source": pk["src"] + " HBM copy",
+                "traffic": None, "kernel_ms": kernel_ms, "note": "achieved uses the UPPER BOUND of gathered bytes (every child row fetched); "
+                "hash-deduplicated children are not fetched, so true traffic is lower"}
+
+    def cpu_baseline(self, budget_s=20.0):
+        import oracle
+        full = self.dataset.cpu().numpy()
+        qs = self.queries[:64].cpu().numpy()
+        t0 = time.time()
+        oracle.knn(full, qs[:4], self.k)
+        per_q = (time.time() - t0) / 4
+        m = int(max(4, min(64, budget_s / max(per_q, 1e-6))))
+        t0 = time.time()
+        oracle.knn(full, qs[:m], self.k)
+        dt = time.time() - t0
+        return {"value": m / dt, "unit": "queries/s", "cores": oracle.num_threads(), "kind": "port",
+                "sample": f"{m} of {self.nq} queries, exact fp32 kNN over all {self.n} rows (oracle/oracle.c, OpenMP)"}
+
+
+WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "cagra": CagraWorkload}
 
 
 METRIC_NAME = "QPS @ recall@10>=0.95 (queries/s of one batched 10k-query search() call; recall@10 in config)"
@@ -378,6 +456,11 @@ def run_ours(args):
             if getattr(args, name):
                 kw[name] = getattr(args, name)
         kw["rank"], kw["world"] = rank, world
+    if args.workload == "cagra":
+        if args.itopk:
+            kw["itopk"] = args.itopk
+        if args.degree:
+            kw["degree"] = args.degree
     wl = WORKLOADS[args.workload](**kw)
     res = Resources()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -513,6 +596,8 @@ def main():
     ap.add_argument("--n-probes", dest="n_probes", type=int, default=0)
     ap.add_argument("--refine-ratio", dest="refine_ratio", type=int, default=0)
     ap.add_argument("--pq-dim", dest="pq_dim", type=int, default=0)
+    ap.add_argument("--itopk", type=int, default=0)
+    ap.add_argument("--degree", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,6 +29,7 @@
 
 #include <cuvs/neighbors/brute_force.h>
 #include <cuvs/neighbors/cagra.h>
+#include <cuvs/neighbors/ivf_flat.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -500,6 +501,48 @@ __global__ void merge_graph_kernel(const uint32_t* __restrict__ fwd, const uint3
   }
 }
 
+
+// ---- graph optimisation (rank-based detour pruning, cpp/src/neighbors/detail/cagra/graph_core.cuh: kern_prune)
+// For node A and its neighbour B at rank kAB, a 2-hop route A -> D -> B is "detourable" when D is a closer neighbour of A
+// (rank kAD < kAB) and B is a neighbour of D with rank kDB < kAB.  Edges with few detours are kept first.
+// One CTA per node; knn rows are sorted by distance (self excluded).
+__global__ void __launch_bounds__(128) detour_count_kernel(const uint32_t* __restrict__ knn, int64_t n, int di, uint32_t* __restrict__ counts)
+{
+  extern __shared__ uint32_t sm[];
+  uint32_t* na  = sm;        // [di] neighbours of A
+  uint32_t* cnt = sm + di;   // [di]
+  const int64_t a = blockIdx.x;
+  for (int j = threadIdx.x; j < di; j += blockDim.x) { na[j] = knn[a * di + j]; cnt[j] = 0; }
+  __syncthreads();
+  for (int kad = 0; kad < di - 1; ++kad) {
+    const uint32_t dn = na[kad];
+    for (int kdb = threadIdx.x; kdb < di; kdb += blockDim.x) {
+      const uint32_t b = knn[static_cast<int64_t>(dn) * di + kdb];
+      const int lo     = max(kad, kdb) + 1;
+      for (int kab = lo; kab < di; ++kab)
+        if (na[kab] == b) { atomicAdd(&cnt[kab], 1u); break; }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < di; j += blockDim.x) counts[a * di + j] = cnt[j];
+}
+
+// keep the `degree` edges with the fewest detours (ties: closer first); one thread per node (di <= 128)
+__global__ void select_pruned_kernel(const uint32_t* __restrict__ knn, const uint32_t* __restrict__ counts, int64_t n, int di, int degree,
+                                     uint32_t* __restrict__ out)
+{
+  int64_t a = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (a >= n) return;
+  const uint32_t* c = counts + a * di;
+  const uint32_t* g = knn + a * di;
+  // counting sort by detour count (counts <= di)
+  int w = 0;
+  for (uint32_t level = 0; level <= static_cast<uint32_t>(di) && w < degree; ++level)
+    for (int j = 0; j < di && w < degree; ++j)
+      if (c[j] == level) out[a * degree + w++] = g[j];
+  for (int j = 0; w < degree; ++j) out[a * degree + w++] = g[j % di];
+}
+
 }  // namespace
 
 // exact kNN graph through the library's own brute-force search (C boundary re-used internally)
@@ -536,6 +579,49 @@ static void build_knn_graph(cuvsResources_t res_h, resources* res, const float* 
   }
   B2_CUDA(cudaStreamSynchronize(res->stream));
   cuvsBruteForceIndexDestroy(bf);
+}
+
+// approximate kNN graph for large inputs: IVF-Flat self-search (k <= 64) in query chunks
+static void build_knn_graph_ivf(cuvsResources_t res_h, resources* res, const float* data, int64_t n, int dim, cuvsDistanceType metric,
+                                int kk, int64_t* knn_out)
+{
+  cuvsIvfFlatIndexParams_t ip = nullptr;
+  cuvsIvfFlatSearchParams_t sp = nullptr;
+  cuvsIvfFlatIndex_t ix = nullptr;
+  auto fail = [&](const char* what) {
+    std::string e = cuvsGetLastErrorText() ? cuvsGetLastErrorText() : "?";
+    if (ix) cuvsIvfFlatIndexDestroy(ix);
+    if (ip) cuvsIvfFlatIndexParamsDestroy(ip);
+    if (sp) cuvsIvfFlatSearchParamsDestroy(sp);
+    B2_FAIL("cagra build: %s failed: %s", what, e.c_str());
+  };
+  if (cuvsIvfFlatIndexParamsCreate(&ip) != CUVS_SUCCESS || cuvsIvfFlatSearchParamsCreate(&sp) != CUVS_SUCCESS || cuvsIvfFlatIndexCreate(&ix) != CUVS_SUCCESS)
+    fail("parameter setup");
+  uint32_t n_lists = 16;
+  while (static_cast<int64_t>(n_lists) * n_lists < n) n_lists *= 2;  // ~sqrt(n), power of two
+  ip->n_lists = n_lists; ip->metric = metric == InnerProduct ? InnerProduct : L2Expanded; ip->kmeans_n_iters = 10;
+  sp->n_probes = std::max<uint32_t>(16, n_lists / 32);
+  int64_t shape[2] = {n, dim};
+  DLManagedTensor ds{};
+  ds.dl_tensor.data = const_cast<float*>(data); ds.dl_tensor.device = DLDevice{kDLCUDA, res->device}; ds.dl_tensor.ndim = 2;
+  ds.dl_tensor.dtype = DLDataType{kDLFloat, 32, 1}; ds.dl_tensor.shape = shape;
+  if (cuvsIvfFlatBuild(res_h, ip, &ds, ix) != CUVS_SUCCESS) fail("kNN stage (ivf_flat build)");
+  const int64_t chunk = 65536;
+  dbuf<float> dist(static_cast<size_t>(chunk) * kk, res->stream);
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    int64_t rows = std::min(chunk, n - r0);
+    int64_t qs[2] = {rows, dim}, os[2] = {rows, kk};
+    DLManagedTensor q = ds, nb{}, dd{};
+    q.dl_tensor.data = const_cast<float*>(data) + r0 * dim; q.dl_tensor.shape = qs;
+    nb.dl_tensor.data = knn_out + r0 * kk; nb.dl_tensor.device = ds.dl_tensor.device; nb.dl_tensor.ndim = 2;
+    nb.dl_tensor.dtype = DLDataType{kDLInt, 64, 1}; nb.dl_tensor.shape = os;
+    dd = nb; dd.dl_tensor.data = dist.data(); dd.dl_tensor.dtype = DLDataType{kDLFloat, 32, 1};
+    if (cuvsIvfFlatSearch(res_h, sp, ix, &q, &nb, &dd, cuvsFilter{0, NO_FILTER}) != CUVS_SUCCESS) fail("kNN stage (ivf_flat search)");
+  }
+  B2_CUDA(cudaStreamSynchronize(res->stream));
+  cuvsIvfFlatIndexDestroy(ix);
+  cuvsIvfFlatIndexParamsDestroy(ip);
+  cuvsIvfFlatSearchParamsDestroy(sp);
 }
 
 }  // namespace b200
@@ -715,23 +801,31 @@ cuvsError_t cuvsCagraBuild(cuvsResources_t res, cuvsCagraIndexParams_t params, D
     B2_EXPECTS(n >= 2 && n < (int64_t(1) << 31), "cagra build: dataset size out of range");
     const int degree = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(params->graph_degree), n - 1));
     B2_EXPECTS(degree >= 1, "graph_degree must be >= 1");
-    // kNN stage (exact; the library's own scan) — k capped by what the fused top-k supports per call
-    const int kk = static_cast<int>(std::min<int64_t>(n, std::min<int64_t>(degree + 1, 24)));
+    // ---- kNN stage through the library's own scans: exact for small inputs, IVF-Flat self-search beyond
+    const int di_want = static_cast<int>(std::max<size_t>(params->intermediate_graph_degree, static_cast<size_t>(degree)));
+    const bool exact  = n <= 65536;
+    const int di      = static_cast<int>(std::min<int64_t>(n - 1, exact ? std::min(di_want, 128) : std::min(di_want, 63)));
+    const int kk      = di + 1;  // + self
     dbuf<float> compact;
     const float* data = idx->data;
-    if (idx->ld != idx->dim) {  // brute force wants unpadded rows
+    if (idx->ld != idx->dim) {  // the scans want unpadded rows
       compact.alloc(static_cast<size_t>(n) * idx->dim, r->stream);
       B2_CUDA(cudaMemcpy2DAsync(compact.data(), sizeof(float) * idx->dim, idx->data, sizeof(float) * idx->ld, sizeof(float) * idx->dim, n,
                                 cudaMemcpyDeviceToDevice, r->stream));
       data = compact.data();
     }
     dbuf<int64_t> knn(static_cast<size_t>(n) * kk, r->stream);
-    build_knn_graph(res, r, data, n, idx->dim, idx->metric, kk, knn.data());
-    // forward edges, then reverse-edge augmentation up to `degree`
+    if (exact) build_knn_graph(res, r, data, n, idx->dim, idx->metric, kk, knn.data());
+    else build_knn_graph_ivf(res, r, data, n, idx->dim, idx->metric, kk, knn.data());
+    // ---- self-free neighbour rows, detour pruning, reverse-edge augmentation
+    dbuf<uint32_t> nbr(static_cast<size_t>(n) * di, r->stream);
+    count_launch(5);
+    knn_to_graph_kernel<<<blocks_for(n, 128), 128, 0, r->stream>>>(knn.data(), n, kk, di, nbr.data(), di);
+    dbuf<uint32_t> counts(static_cast<size_t>(n) * di, r->stream);
+    detour_count_kernel<<<static_cast<unsigned>(n), 128, sizeof(uint32_t) * 2 * di, r->stream>>>(nbr.data(), n, di, counts.data());
     dbuf<uint32_t> fwd(static_cast<size_t>(n) * degree, r->stream);
-    const int keep = std::min(kk - 1 > 0 ? kk - 1 : 1, std::max(1, degree / 2));
-    count_launch(3);
-    knn_to_graph_kernel<<<blocks_for(n, 128), 128, 0, r->stream>>>(knn.data(), n, kk, keep, fwd.data(), degree);
+    select_pruned_kernel<<<blocks_for(n, 128), 128, 0, r->stream>>>(nbr.data(), counts.data(), n, di, degree, fwd.data());
+    const int keep    = std::max(1, degree / 2);
     const int rev_cap = degree;
     dbuf<uint32_t> rev(static_cast<size_t>(n) * rev_cap, r->stream), rev_cnt(static_cast<size_t>(n), r->stream);
     B2_CUDA(cudaMemsetAsync(rev_cnt.data(), 0, sizeof(uint32_t) * n, r->stream));
