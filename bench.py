@@ -162,6 +162,7 @@ class BruteForceWorkload:
 
     def cpu_baseline(self, budget_s=20.0):
         import oracle
+        oracle.set_threads(os.cpu_count() or 1)
         ds = self.dataset.cpu().numpy()
         qs = self.queries[:64].cpu().numpy()
         t0 = time.time()
@@ -328,6 +329,7 @@ class IvfPqWorkload:
 
     def cpu_baseline(self, budget_s=20.0):
         import oracle
+        oracle.set_threads(os.cpu_count() or 1)
         ds = self.dataset[:1_000_000].cpu().numpy()
         qs = self.queries[:64].cpu().numpy()
         t0 = time.time()
@@ -408,6 +410,7 @@ class CagraWorkload:
 
     def cpu_baseline(self, budget_s=20.0):
         import oracle
+        oracle.set_threads(os.cpu_count() or 1)
         full = self.dataset.cpu().numpy()
         qs = self.queries[:64].cpu().numpy()
         t0 = time.time()
@@ -542,6 +545,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     wl = args.workload
     n = args.n or (10_000_000 if wl == "ivf_pq" else 1_000_000)
     d, nq, k = 128, args.nq or 10_000, 10

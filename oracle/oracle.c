@@ -512,6 +512,15 @@ void oracle_kmeans_assign(const float* x, int64_t n, const float* c, int kc, int
   free(cn);
 }
 
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
