@@ -430,6 +430,19 @@ WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "cagra"
 METRIC_NAME = "QPS @ recall@10>=0.95 (queries/s of one batched 10k-query search() call; recall@10 in config)"
 
 
+def ncu_traffic(workload, wl):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by scripts/ncu_summary.py); only valid for the configuration it was captured on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        ent = json.load(open(path)).get(workload)
+    except (OSError, ValueError):
+        return None
+    if not ent or ent.get("n") != getattr(wl, "n", None) or ent.get("world", 1) != getattr(wl, "world", 1):
+        return None
+    return ent.get("dram_bytes_per_launch")
+
+
 def launches():
     from cuvs_b200._capi import lib
     lib.cuvsB200KernelLaunches.restype = C.c_longlong
@@ -493,9 +506,14 @@ def run_ours(args):
     lib.cuvsB200TimingReset()
     lib.cuvsB200TimingEnable(1)
     l0 = launches()
+    prof = os.environ.get("CUVS_B200_PROFILE") == "1"      # ncu --profile-from-start off: only the timed steps
     with ClockSampler(local) as clk:
         barrier()
+        if prof:
+            torch.cuda.profiler.start()
         ms = timed(wl.step, args.steps)
+        if prof:
+            torch.cuda.profiler.stop()
         barrier()
     n_launch = launches() - l0
     lib.cuvsB200TimingEnable(0)
@@ -530,6 +548,7 @@ def run_ours(args):
             "gpu_launches": n_launch, "parity_spot_check": ok,
             "roofline": wl.roofline(kernel_ms, pk),
         }
+        line["roofline"]["traffic"] = ncu_traffic(args.workload, wl)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = wl.cpu_baseline()
         print(json.dumps(line))

@@ -52,7 +52,7 @@ struct bf_index {
   int Kp       = 0;
   int64_t rows_pad = 0;
   owned<__nv_bfloat16> hi, lo;
-  owned<float> hn;
+  owned<__nv_bfloat16> hx;  // [rows_pad, 16] half-norm plane (scan_tc.cuh)
   owned<float> inv_norm;  // cosine only
 };
 
@@ -171,7 +171,7 @@ static bf_index* bf_build(resources* res, const DLTensor& ds, cuvsDistanceType m
     idx->rows_pad = tc_pad_rows(idx->n);
     idx->hi.alloc(static_cast<size_t>(idx->rows_pad) * idx->Kp);
     idx->lo.alloc(static_cast<size_t>(idx->rows_pad) * idx->Kp);
-    idx->hn.alloc(static_cast<size_t>(idx->rows_pad));
+    idx->hx.alloc(static_cast<size_t>(idx->rows_pad) * 16);
     const float* scale = nullptr;
     if (metric == CosineExpanded) {
       idx->inv_norm.alloc(static_cast<size_t>(idx->n));
@@ -181,7 +181,7 @@ static bf_index* bf_build(resources* res, const DLTensor& ds, cuvsDistanceType m
     }
     tc_split_planes(stream, idx->data, idx->n, idx->d, idx->d, idx->Kp, idx->hi.data(), idx->lo.data(), idx->rows_pad, scale);
     const bool l2 = (metric != InnerProduct && metric != CosineExpanded);
-    tc_half_norms(stream, l2 ? idx->norms.data() : nullptr, idx->n, idx->rows_pad, idx->hn.data());
+    tc_half_norms(stream, l2 ? idx->norms.data() : nullptr, idx->n, idx->rows_pad, idx->hx.data());
   }
   return idx.release();
 }
@@ -263,7 +263,7 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
   tc_bound bnd;
   bnd.keys = bkeys.data();
   tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
-               idx.hn.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd);
+               idx.hx.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd);
   if (row_stride > KC) {
     out.score.alloc(static_cast<size_t>(nq) * KC, stream);
     out.pos.alloc(static_cast<size_t>(nq) * KC, stream);

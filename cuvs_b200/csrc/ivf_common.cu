@@ -45,53 +45,70 @@ __global__ void first_of_rows_kernel(const uint32_t* __restrict__ pos, const flo
 }
 
 // ---- probe bucketing -----------------------------------------------------------------------
-// probes of empty lists (e.g. lists owned by another shard) are dropped here
-__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, const int64_t* __restrict__ list_offsets,
-                                    uint32_t* __restrict__ counts)
+// Pairs are bucketed by (list, near/far bin): bin 0 holds a query's nearest `near_ranks` probes.  Inside a list the near
+// pairs come first, so each list's FIRST 128-pair work item holds the lowest probe ranks; all first items are scheduled
+// before any other item.  The per-query pruning bound (tc_bound) is therefore already tight — every query's closest
+// lists have been scanned — when the bulk of the work starts, and the epilogue's insert path is rarely taken.
+// Probes of empty lists (e.g. lists owned by another shard) are dropped here.
+__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int near_ranks,
+                                    const int64_t* __restrict__ list_offsets, uint32_t* __restrict__ counts)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
   uint32_t l = probes[t];
-  if (l != 0xffffffffu && list_offsets[l + 1] > list_offsets[l]) atomicAdd(&counts[l], 1u);
+  if (l != 0xffffffffu && list_offsets[l + 1] > list_offsets[l])
+    atomicAdd(&counts[2 * l + (static_cast<int>(t % n_probes) < near_ranks ? 0 : 1)], 1u);
 }
 
-// single CTA: exclusive scans over lists of (a) pair counts, (b) item counts ceil(cnt/128)
+// single CTA: exclusive scans over lists of (a) pair counts, (b) "has a first item", (c) further items ceil(cnt/128) - 1
 __global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __restrict__ counts, int64_t n_lists,
-                                                           uint32_t* __restrict__ pair_off, uint32_t* __restrict__ item_off,
-                                                           int* __restrict__ n_items, uint32_t* __restrict__ cursor)
+                                                           uint32_t* __restrict__ pair_off, uint32_t* __restrict__ first_off,
+                                                           uint32_t* __restrict__ rest_off, int* __restrict__ n_items,
+                                                           uint32_t* __restrict__ cursor)
 {
-  __shared__ uint32_t s_pairs[1024], s_items[1024];
-  __shared__ uint32_t run_pairs, run_items;
-  if (threadIdx.x == 0) { run_pairs = 0; run_items = 0; }
+  __shared__ uint32_t s_pairs[1024], s_first[1024], s_rest[1024];
+  __shared__ uint32_t run_pairs, run_first, run_rest;
+  if (threadIdx.x == 0) { run_pairs = 0; run_first = 0; run_rest = 0; }
   __syncthreads();
   for (int64_t base = 0; base < n_lists; base += 1024) {
-    int64_t l  = base + threadIdx.x;
-    uint32_t c = l < n_lists ? counts[l] : 0;
-    uint32_t g = (c + 127) / 128;
+    int64_t l   = base + threadIdx.x;
+    uint32_t c0 = l < n_lists ? counts[2 * l] : 0;
+    uint32_t c  = c0 + (l < n_lists ? counts[2 * l + 1] : 0);
+    uint32_t f  = c > 0 ? 1u : 0u;
+    uint32_t g  = c > 0 ? (c + 127) / 128 - 1 : 0u;
     s_pairs[threadIdx.x] = c;
-    s_items[threadIdx.x] = g;
+    s_first[threadIdx.x] = f;
+    s_rest[threadIdx.x]  = g;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
-      uint32_t a = threadIdx.x >= o ? s_pairs[threadIdx.x - o] : 0;
-      uint32_t b = threadIdx.x >= o ? s_items[threadIdx.x - o] : 0;
+      uint32_t a = 0, b = 0, d = 0;
+      if (threadIdx.x >= o) { a = s_pairs[threadIdx.x - o]; b = s_first[threadIdx.x - o]; d = s_rest[threadIdx.x - o]; }
       __syncthreads();
       s_pairs[threadIdx.x] += a;
-      s_items[threadIdx.x] += b;
+      s_first[threadIdx.x] += b;
+      s_rest[threadIdx.x]  += d;
       __syncthreads();
     }
     if (l < n_lists) {
-      pair_off[l] = run_pairs + s_pairs[threadIdx.x] - c;
-      item_off[l] = run_items + s_items[threadIdx.x] - g;
-      cursor[l]   = 0;
+      pair_off[2 * l]     = run_pairs + s_pairs[threadIdx.x] - c;
+      pair_off[2 * l + 1] = run_pairs + s_pairs[threadIdx.x] - c + c0;
+      first_off[l]        = run_first + s_first[threadIdx.x] - f;
+      rest_off[l]         = run_rest + s_rest[threadIdx.x] - g;
+      cursor[2 * l]       = 0;
+      cursor[2 * l + 1]   = 0;
     }
     __syncthreads();
-    if (threadIdx.x == 1023) { run_pairs += s_pairs[1023]; run_items += s_items[1023]; }
+    if (threadIdx.x == 1023) { run_pairs += s_pairs[1023]; run_first += s_first[1023]; run_rest += s_rest[1023]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { n_items[0] = static_cast<int>(run_items); n_items[1] = static_cast<int>(run_pairs); }
+  if (threadIdx.x == 0) {
+    n_items[0] = static_cast<int>(run_first + run_rest);
+    n_items[1] = static_cast<int>(run_pairs);
+    n_items[2] = static_cast<int>(run_first);
+  }
 }
 
-__global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes,
+__global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int near_ranks,
                                       const int64_t* __restrict__ list_offsets, const uint32_t* __restrict__ pair_off,
                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_of,
                                       uint32_t* __restrict__ pair_query, uint32_t* __restrict__ pair_list)
@@ -100,31 +117,34 @@ __global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64
   if (t >= total) return;
   uint32_t l = probes[t];
   if (l == 0xffffffffu || list_offsets[l + 1] <= list_offsets[l]) { slot_of[t] = 0xffffffffu; return; }
-  uint32_t slot    = pair_off[l] + atomicAdd(&cursor[l], 1u);
+  const uint32_t b = 2 * l + (static_cast<int>(t % n_probes) < near_ranks ? 0 : 1);
+  uint32_t slot    = pair_off[b] + atomicAdd(&cursor[b], 1u);
   slot_of[t]       = slot;
   pair_query[slot] = static_cast<uint32_t>(t / n_probes);
   pair_list[slot]  = l;
 }
 
 __global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ pair_off,
-                                       const uint32_t* __restrict__ item_off, const int64_t* __restrict__ list_offsets,
+                                       const uint32_t* __restrict__ first_off, const uint32_t* __restrict__ rest_off,
+                                       const int* __restrict__ n_items, const int64_t* __restrict__ list_offsets,
                                        int64_t n_lists, int KC, tc_item* __restrict__ items)
 {
   int64_t l = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (l >= n_lists) return;
-  uint32_t c = counts[l];
+  uint32_t c = counts[2 * l] + counts[2 * l + 1];
   if (c == 0) return;
   const uint32_t b_row0  = static_cast<uint32_t>(list_offsets[l]);
   const uint32_t n_tiles = static_cast<uint32_t>((list_offsets[l + 1] - list_offsets[l]) / 128);
+  const uint32_t n_first = static_cast<uint32_t>(n_items[2]);
   uint32_t g = (c + 127) / 128;
   for (uint32_t j = 0; j < g; ++j) {
     tc_item it;
-    it.a_row0     = pair_off[l] + j * 128;
+    it.a_row0     = pair_off[2 * l] + j * 128;
     it.b_row0     = b_row0;
     it.n_tiles    = n_tiles;
     it.valid_rows = min(128u, c - j * 128);
     it.out_off    = static_cast<uint64_t>(it.a_row0) * KC;
-    items[item_off[l] + j] = it;
+    items[j == 0 ? first_off[l] : n_first + rest_off[l] + (j - 1)] = it;
   }
 }
 
@@ -244,9 +264,9 @@ void tc_rows::build(cudaStream_t s, const float* x, int64_t n_, int d_, const fl
   rows_pad = tc_pad_rows(std::max<int64_t>(n, 1));
   hi.alloc(static_cast<size_t>(rows_pad) * Kp);
   if (with_lo) lo.alloc(static_cast<size_t>(rows_pad) * Kp); else lo.release();
-  hn.alloc(static_cast<size_t>(rows_pad));
+  hx.alloc(static_cast<size_t>(rows_pad) * 16);
   tc_split_planes(s, x, n, d, d, Kp, hi.data(), with_lo ? lo.data() : nullptr, rows_pad, row_scale);
-  tc_half_norms(s, xn, n, rows_pad, hn.data());
+  tc_half_norms(s, xn, n, rows_pad, hx.data());
 }
 
 void tc_rows_tmp::build(cudaStream_t s, const float* x, int64_t n_, int d_, bool with_lo, int64_t extra_pad_rows,
@@ -276,7 +296,7 @@ void coarse_select(resources* res, const tc_rows_tmp& q, const tc_rows& centers,
   dbuf<float> scores(static_cast<size_t>(nq_pad) * ld, s);
   const bool three = q.lo.data() != nullptr && centers.lo.data() != nullptr;
   tc_scan_topk(s, res->device, q.hi.data(), q.lo.data(), q.rows_pad, centers.hi.data(), centers.lo.data(), centers.rows_pad,
-               q.Kp, centers.hn.data(), items.data(), m_tiles, nullptr, 0, three ? 3 : 1, scores.data(), nullptr, ld);
+               q.Kp, centers.hx.data(), items.data(), m_tiles, nullptr, 0, three ? 3 : 1, scores.data(), nullptr, ld);
   dbuf<float> tmp_scores;
   if (!probe_scores) { tmp_scores.alloc(static_cast<size_t>(q.n) * n_probes, s); probe_scores = tmp_scores.data(); }
   select_k(s, scores.data(), nullptr, IDX_NONE, q.n, centers.n, ld, n_probes, probe_scores, probes, IDX_U32, true);
@@ -304,7 +324,7 @@ void assign_nearest(resources* res, const __nv_bfloat16* x_hi, const __nv_bfloat
                                                                 static_cast<uint32_t>(centers.rows_pad / 128), KCW);
     B2_CUDA(cudaGetLastError());
     tc_scan_topk(s, res->device, x_hi + r0 * Kp, x_lo ? x_lo + r0 * Kp : nullptr, x_rows_pad - r0, centers.hi.data(),
-                 centers.lo.data(), centers.rows_pad, Kp, centers.hn.data(), items.data(), m_tiles, nullptr, KC,
+                 centers.lo.data(), centers.rows_pad, Kp, centers.hx.data(), items.data(), m_tiles, nullptr, KC,
                  three ? 3 : 1, cs.data(), cp.data(), KCW);
     count_launch();
     first_of_rows_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(cp.data(), cs.data(), rows, KC, lists, labels + r0,
@@ -324,17 +344,20 @@ void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_pro
   out.pair_query.alloc(static_cast<size_t>(total), s);
   out.pair_list.alloc(static_cast<size_t>(total), s);
   out.items.alloc(static_cast<size_t>(out.max_items), s);
-  out.n_items.alloc(2, s);
-  dbuf<uint32_t> counts(static_cast<size_t>(n_lists), s), pair_off(static_cast<size_t>(n_lists), s),
-    item_off(static_cast<size_t>(n_lists), s), cursor(static_cast<size_t>(n_lists), s);
-  B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * n_lists, s));
+  out.n_items.alloc(4, s);
+  const int near_ranks = std::max(1, n_probes / 8);
+  dbuf<uint32_t> counts(static_cast<size_t>(2 * n_lists), s), pair_off(static_cast<size_t>(2 * n_lists), s),
+    first_off(static_cast<size_t>(n_lists), s), rest_off(static_cast<size_t>(n_lists), s), cursor(static_cast<size_t>(2 * n_lists), s);
+  B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * 2 * n_lists, s));
   count_launch(4);
-  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, list_offsets_dev, counts.data());
-  scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), item_off.data(), out.n_items.data(), cursor.data());
-  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, list_offsets_dev, pair_off.data(), cursor.data(),
-                                                                out.slot_of.data(), out.pair_query.data(), out.pair_list.data());
-  make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), item_off.data(),
-                                                                   list_offsets_dev, n_lists, KC, out.items.data());
+  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, near_ranks, list_offsets_dev, counts.data());
+  scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), first_off.data(), rest_off.data(), out.n_items.data(),
+                                       cursor.data());
+  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, near_ranks, list_offsets_dev, pair_off.data(),
+                                                                cursor.data(), out.slot_of.data(), out.pair_query.data(),
+                                                                out.pair_list.data());
+  make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), first_off.data(), rest_off.data(),
+                                                                   out.n_items.data(), list_offsets_dev, n_lists, KC, out.items.data());
   B2_CUDA(cudaGetLastError());
 }
 

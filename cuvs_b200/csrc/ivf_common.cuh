@@ -24,7 +24,7 @@ struct tc_rows {
   int64_t n = 0, rows_pad = 0;
   int d = 0, Kp = 0;
   owned<__nv_bfloat16> hi, lo;
-  owned<float> hn;
+  owned<__nv_bfloat16> hx;  // [rows_pad, 16] half-norm plane
   void build(cudaStream_t s, const float* x, int64_t n_, int d_, const float* xn /*|x|^2 or null => hn = 0*/, bool with_lo,
              const float* row_scale = nullptr);
 };

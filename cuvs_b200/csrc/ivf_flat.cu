@@ -49,7 +49,7 @@ struct ivf_flat_index {
   owned<int64_t> ids;        // [rows_total], -1 on padding rows
   owned<float> xn;           // [rows_total] |x|^2 (cosine / certificate use)
   owned<__nv_bfloat16> hi;   // [rows_total, Kp] bf16 rows (normalised for cosine)
-  owned<float> hn;           // [rows_total] |x|^2/2, +inf on padding rows
+  owned<__nv_bfloat16> hx;   // [rows_total, 16] half-norm plane: |x|^2/2, +inf on padding rows (scan_tc.cuh)
   int Kp = 0;
 };
 
@@ -122,7 +122,7 @@ void refresh_tc_side(resources* res, ivf_flat_index& idx)
   const int64_t R = idx.lists.rows_total;
   idx.Kp          = tc_pad_k(idx.dim);
   idx.hi.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * idx.Kp);
-  idx.hn.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)));
+  idx.hx.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * 16);
   idx.xn.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)));
   if (R == 0) return;
   row_norms(s, idx.data.data(), R, idx.dim, idx.dim, idx.xn.data());
@@ -134,8 +134,10 @@ void refresh_tc_side(resources* res, ivf_flat_index& idx)
   }
   tc_split_planes(s, idx.data.data(), R, idx.dim, idx.dim, idx.Kp, idx.hi.data(), nullptr, R, scale.data());
   count_launch();
-  half_norms_masked_kernel<<<blocks_for(R, 256), 256, 0, s>>>(idx.xn.data(), idx.ids.data(), R, !is_l2(idx.metric), idx.hn.data());
+  dbuf<float> hn(static_cast<size_t>(R), s);
+  half_norms_masked_kernel<<<blocks_for(R, 256), 256, 0, s>>>(idx.xn.data(), idx.ids.data(), R, !is_l2(idx.metric), hn.data());
   B2_CUDA(cudaGetLastError());
+  tc_pack_half_norms(s, hn.data(), R, idx.hx.data());
 }
 
 void refresh_centers_tc(resources* res, ivf_flat_index& idx)
@@ -322,7 +324,7 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
     bnd.idx  = pb.pair_query.data();
     timed_section ts("ivf_flat_scan", s);
     tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.hi.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                 idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
+                 idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
   }
 
   // ---- 4. per query: merge probes by approximate score, exact re-score, ids

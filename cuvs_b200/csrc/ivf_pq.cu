@@ -67,7 +67,7 @@ struct ivf_pq_index {
   // decoded side (path B)
   int Kp = 0;
   owned<__nv_bfloat16> yhat;  // [rows_total, Kp]
-  owned<float> hn;            // [rows_total] |y|^2/2 (0 for inner product), +inf on padding rows
+  owned<__nv_bfloat16> hx;    // [rows_total, 16] half-norm plane: |y|^2/2 (0 for inner product), +inf on padding rows
   int book() const { return 1 << pq_bits; }
 };
 
@@ -548,17 +548,19 @@ void refresh_decoded(resources* res, ivf_pq_index& idx)
   auto s          = res->stream;
   const int64_t R = idx.lists.rows_total;
   idx.Kp          = tc_pad_k(idx.rot_dim);
-  if (idx.conservative || !tc_supported(res->device, idx.rot_dim)) { idx.yhat.release(); idx.hn.release(); return; }
+  if (idx.conservative || !tc_supported(res->device, idx.rot_dim)) { idx.yhat.release(); idx.hx.release(); return; }
   idx.yhat.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * idx.Kp);
-  idx.hn.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)));
+  idx.hx.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * 16);
   if (R == 0) return;
+  dbuf<float> hn(static_cast<size_t>(R), s);
   count_launch();
   pq_decode_kernel<<<blocks_for(R * 32, 256), 256, 0, s>>>(idx.codes.data(), idx.ids.data(), R, idx.pq_dim, idx.pq_len, idx.book(),
                                                            idx.Kp, idx.pq_centers.data(),
                                                            idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_CLUSTER,
                                                            idx.lists.d_offsets.data(), idx.n_lists, is_ip(idx.metric),
-                                                           idx.centers_rot.data(), idx.rot_dim, idx.yhat.data(), idx.hn.data());
+                                                           idx.centers_rot.data(), idx.rot_dim, idx.yhat.data(), hn.data());
   B2_CUDA(cudaGetLastError());
+  tc_pack_half_norms(s, hn.data(), R, idx.hx.data());
 }
 
 void train_codebooks(resources* res, ivf_pq_index& idx, const float* resid, const uint32_t* labels, int64_t n, int n_iters)
@@ -810,9 +812,10 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
       bnd.idx   = pb.pair_query.data();
       bnd.add   = add.data();
       bnd.scale = scale;
+      bnd.kth   = k;  // only the query's k best survive the merge below
       timed_section ts("pq_scan", s);
       tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                   idx.Kp, idx.hn.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
+                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
     }
   } else {
     const int book      = idx.book();

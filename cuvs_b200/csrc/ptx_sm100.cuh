@@ -168,6 +168,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
   return d;
 }
+// K-major operand tile, 32-byte swizzle: rows of 32 bytes (one K=16 bf16 step), 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr)
+{
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;  // SWIZZLE_32B
+  return d;
+}
 // kind::f16, A = B = bf16, D = fp32, both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
 {

@@ -7,17 +7,19 @@
 //   unfused distance-NN       cpp/src/distance/unfused_distance_nn.cuh:54-118
 // with one warp-specialised persistent kernel:
 //
-//   warp 0   TMA producer : query tile (A, resident per work item) + dataset k-blocks (B ring)
-//   warp 1   MMA issuer   : tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), 128x128 tiles,
-//                           split-bf16 products hi*hi + lo*hi + hi*lo  (passes = 3) or hi*hi (passes = 1)
-//   warps 2-5 epilogue    : tcgen05.ld one accumulator row per thread, s = hn[col] - acc, compare with
-//                           the thread's running k'-th best, rare inserts go through a per-thread smem
-//                           queue and are merged into a sorted register list warp-convergently.
+//   warp 0     TMA producer : query tile (A, resident per work item) + dataset k-blocks (B ring)
+//   warp 1     MMA issuer   : tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), 128x128 tiles,
+//                             split-bf16 products hi*hi + lo*hi + hi*lo  (passes = 3) or hi*hi (passes = 1),
+//                             plus ONE extra K=16 step per tile that adds -|x|^2/2 (three bf16 pieces of the fp32
+//                             half-norm times a constant column of ones), so the accumulator already holds
+//                             t = q.x - |x|^2/2 = -(score) and the epilogue has no per-element arithmetic left
+//   warps 2-9  epilogue     : tcgen05.ld one accumulator row per thread (two warps per TMEM lane quarter, 64 columns
+//                             each), release the TMEM buffer, then a max-tree per 32 columns against the row's running
+//                             threshold; the rare hits go through a per-thread smem queue into a sorted register list.
 //
-// The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps
-// the MMAs of tile t+1.  Nothing but the k' (score, position) pairs per query row ever leaves the SM:
-// the n x nq distance matrix of the reference's unfused path (n*nq*4 bytes through HBM) is never
-// materialised.
+// The accumulator ring is 4 x 128 TMEM columns (all 512), so MMAs run up to three tiles ahead of the slowest
+// epilogue warp.  Nothing but the k' (score, position) pairs per query row ever leaves the SM: the n x nq distance
+// matrix of the reference's unfused path (n*nq*4 bytes through HBM) is never materialised.
 #include "common.hpp"
 #include "ptx_sm100.cuh"
 #include "scan_tc.cuh"
@@ -32,58 +34,61 @@
 namespace b200 {
 namespace {
 
-constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kChunk     = 16;         // accumulator columns per tcgen05.ld
-constexpr int kQueue     = 24;         // per-thread pending-insert queue; flushed (warp-convergently) when > kQueue - kChunk
+constexpr int kTileBytes  = 128 * 128;  // 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int kExtBytes   = 128 * 32;   // 128 rows x 16 bf16, SWIZZLE_32B (the half-norm K extension)
+constexpr int kQueue      = 16;         // per-thread pending-insert queue entries
+constexpr int kAccBufs    = 4;          // TMEM accumulator ring
+constexpr int kEpiWarps   = 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kCols       = 64;         // accumulator columns per epilogue thread and tile
 
-template <int KB, int NPL, int EPIW>
+template <int KB, int NPL>
 struct cfg {
-  static constexpr int threads     = 64 + 32 * EPIW;
+  static constexpr int threads     = 64 + kEpiThreads;
   static constexpr int stages      = NPL == 2 ? 3 : 6;
   static constexpr int a_bytes     = NPL * KB * kTileBytes;
-  static constexpr int stage_bytes = NPL * kTileBytes;
-  static constexpr int n_bars      = 2 * stages + 2 + 4;
-  static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + stages * stage_bytes + EPIW * 2 * (512 / EPIW) * 4 /*hn, per warp*/ +
-                                 kQueue * (32 * EPIW) * 8 /*queues*/ + n_bars * 8 + 16;
+  static constexpr int stage_bytes = NPL * kTileBytes + kExtBytes;  // ext slot used by the kb == 0 stage of a tile
+  static constexpr int n_bars      = 2 * stages + 2 + 2 * kAccBufs;
+  static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + kExtBytes /*ones*/ + stages * stage_bytes +
+                                 kQueue * kEpiThreads * 8 /*queues*/ + n_bars * 8 + 16;
 };
 
-// KC > 0: fused top-KC epilogue.  KC == 0: "store" epilogue — every score of the tile is written to
+// KC > 0: fused top-KC epilogue, two candidate lists per (item, query row) — one per 64-column half of the tiles.
+// KC == 0: "store" epilogue — every score of the tile is written to
 // out_score[out_off + row * out_row_stride + (column within the item's range)] (dense distance block).
-// EPIW = 4: one epilogue warp per TMEM lane quarter (128 columns each); EPIW = 8: two per quarter
-// (64 columns each, two candidate lists per query row and item).
-template <int KB, int NPL, int KC, int EPIW>
-__global__ void __launch_bounds__(64 + 32 * EPIW, 1)
+template <int KB, int NPL, int KC>
+__global__ void __launch_bounds__(64 + kEpiThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const float* __restrict__ hn, const tc_item* __restrict__ items, int n_items_host,
+               const __grid_constant__ CUtensorMap tmB_x, const tc_item* __restrict__ items, int n_items_host,
                const int* __restrict__ n_items_dev, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
                int64_t out_row_stride, int dbg_skip_epilogue, tc_bound bound)
 {
-  using C = cfg<KB, NPL, EPIW>;
-  constexpr int kEpiThreads = 32 * EPIW;
+  using C = cfg<KB, NPL>;
   const int n_items = n_items_dev ? *n_items_dev : n_items_host;
   // 1024-byte alignment is what SWIZZLE_128B operand tiles need; declared on the array (no integer
   // round-trip of the pointer) so that the compiler keeps every access in the shared address space.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (threadIdx.x == 0 && (ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint8_t* sA   = smem_raw;
-  uint8_t* sB   = sA + C::a_bytes;
-  float* sHn    = reinterpret_cast<float*>(sB + C::stages * C::stage_bytes);  // [EPIW warps][2 buffers][512/EPIW columns]
-  uint2* qe     = reinterpret_cast<uint2*>(sHn + EPIW * 2 * (512 / EPIW));      // [kQueue][kEpiThreads] {packed score, group base row}
+  uint8_t* sA    = smem_raw;
+  uint8_t* sOnes = sA + C::a_bytes;
+  uint8_t* sB    = sOnes + kExtBytes;
+  uint2* qe      = reinterpret_cast<uint2*>(sB + C::stages * C::stage_bytes);  // [kQueue][kEpiThreads] {t bits, row position}
   uint64_t* bars = reinterpret_cast<uint64_t*>(qe + kQueue * kEpiThreads);
   uint64_t* full    = bars;
   uint64_t* empty   = bars + C::stages;
   uint64_t* a_full  = bars + 2 * C::stages;
   uint64_t* a_empty = a_full + 1;
-  uint64_t* tfull   = a_empty + 1;  // [2]
-  uint64_t* tempty  = tfull + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull   = a_empty + 1;       // [kAccBufs]
+  uint64_t* tempty  = tfull + kAccBufs;  // [kAccBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA_hi);
     ptx::prefetch_tmap(&tmB_hi);
+    ptx::prefetch_tmap(&tmB_x);
     if (NPL == 2) {
       ptx::prefetch_tmap(&tmA_lo);
       ptx::prefetch_tmap(&tmB_lo);
@@ -96,13 +101,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAccBufs; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], kEpiThreads);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) { ptx::tmem_alloc<256>(tmem_slot); }
+  // the constant A-side operand of the half-norm step: every row = {1, 1, 1, 0, 0, 0, 0, 0} in BOTH 16-byte chunks
+  // (identical chunks make the tile invariant under the 32-byte swizzle; the B side has zeros in its second chunk)
+  if (threadIdx.x < kExtBytes / 16)
+    reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);
+  ptx::fence_proxy_async();
+  if (warp == 2) { ptx::tmem_alloc<128 * kAccBufs>(tmem_slot); }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -128,10 +138,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full[stage], C::stage_bytes);
+            ptx::mbar_arrive_expect_tx(&full[stage], NPL * kTileBytes + (kb == 0 ? kExtBytes : 0));
             uint8_t* dst = sB + stage * C::stage_bytes;
             ptx::tma_load_2d(dst, &tmB_hi, &full[stage], kb * 64, brow);
             if (NPL == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
+            if (kb == 0) ptx::tma_load_2d(dst + NPL * kTileBytes, &tmB_x, &full[stage], 0, brow);
             if (++stage == C::stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -142,6 +153,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
       const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
+      const uint64_t ones   = ptx::make_smem_desc_sw32(ptx::smem_u32(sOnes));
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const uint32_t n_tiles = items[it].n_tiles;
@@ -168,70 +180,61 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 ptx::mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
               }
             }
+            if (kb == 0) ptx::mma_bf16_ss(d_tmem, ones, ptx::make_smem_desc_sw32(bs + NPL * kTileBytes), idesc, 1u);  // -= |x|^2/2
             ptx::mma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
             if (++stage == C::stages) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
         }
         ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
         a_phase ^= 1;
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (EPIW warps, 1 row x (512/EPIW) columns per thread)
+    // ------------------------------------------------------------------ epilogue (8 warps, 1 row x 64 columns per thread)
     const int quarter = warp & 3;             // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int row     = quarter * 32 + lane;  // accumulator row == query row within the tile
-    const int half    = (warp - 2) >> 2;      // which column range of the tile (0 when EPIW == 4)
+    const int half    = (warp - 2) >> 2;      // which 64-column half of the tile
     const int et      = half * 128 + row;     // slot in the queue arrays
-    constexpr int kCols   = 512 / EPIW;       // columns per thread and tile
-    constexpr int kChunks = kCols / kChunk;
-    const int col0        = half * kCols;
+    const int col0    = half * kCols;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
     uint32_t acc = 0, acc_phase = 0;
+
+    // One tile: wait for the accumulator, pull this thread's 64 columns into registers, hand the TMEM buffer back.
+    auto fetch_tile = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      ptx::tmem_ld_32x32(t_lane + acc * 128, v0);
+      ptx::tmem_ld_32x32(t_lane + acc * 128 + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&tempty[acc]);
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
+    };
+
     if constexpr (KC == 0) {
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const tc_item item   = items[it];
-        float* hn_w          = sHn + (warp - 2) * 2 * kCols;
-        const float* hn_item = hn + item.b_row0 + col0;
-        float4 hn_reg        = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + lane * 4);
-        float* orow          = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride;
-        const bool live      = static_cast<uint32_t>(row) < item.valid_rows;
+        const tc_item item = items[it];
+        float* orow        = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride + col0;
+        const bool live    = static_cast<uint32_t>(row) < item.valid_rows;
         for (uint32_t t = 0; t < item.n_tiles; ++t) {
-          if (lane < kCols / 4) *reinterpret_cast<float4*>(hn_w + acc * kCols + lane * 4) = hn_reg;
-          __syncwarp();
-          if (t + 1 < item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + (t + 1) * 128 + lane * 4);
-          ptx::mbar_wait(&tfull[acc], acc_phase);
-          ptx::tc_fence_after_sync();
-#pragma unroll 1
-          for (int ch = 0; ch < kChunks; ++ch) {
-            uint32_t v[kChunk];
-            const int c0 = col0 + ch * kChunk;
-            ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + c0, v);
-            ptx::tmem_ld_wait();
-            if (live) {
-              const float4* h4 = reinterpret_cast<const float4*>(hn_w + acc * kCols + ch * kChunk);
-              float4* o4       = reinterpret_cast<float4*>(orow + t * 128 + c0);
+          uint32_t v0[32], v1[32];
+          fetch_tile(v0, v1);
+          if (live) {
+            float4* o4 = reinterpret_cast<float4*>(orow + t * 128);
 #pragma unroll
-              for (int c4 = 0; c4 < kChunk / 4; ++c4) {
-                const float4 h = h4[c4];
-                o4[c4] = make_float4(h.x - __uint_as_float(v[c4 * 4 + 0]), h.y - __uint_as_float(v[c4 * 4 + 1]),
-                                     h.z - __uint_as_float(v[c4 * 4 + 2]), h.w - __uint_as_float(v[c4 * 4 + 3]));
-              }
+            for (int c4 = 0; c4 < 8; ++c4) {
+              o4[c4]     = make_float4(-__uint_as_float(v0[c4 * 4 + 0]), -__uint_as_float(v0[c4 * 4 + 1]),
+                                       -__uint_as_float(v0[c4 * 4 + 2]), -__uint_as_float(v0[c4 * 4 + 3]));
+              o4[8 + c4] = make_float4(-__uint_as_float(v1[c4 * 4 + 0]), -__uint_as_float(v1[c4 * 4 + 1]),
+                                       -__uint_as_float(v1[c4 * 4 + 2]), -__uint_as_float(v1[c4 * 4 + 3]));
             }
           }
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&tempty[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
         }
       }
     } else {
-      // Fused top-KC.  The low 4 mantissa bits of every score carry the column index inside its group of 16
-      // (a <= 2^-19 relative perturbation, covered by the certificate's eps), so a queue entry is one 64-bit
-      // store {packed score, group base row} and the min-tree doubles as an arg-min.
-      float* hn_w = sHn + (warp - 2) * 2 * kCols;  // this warp's private staging of the tile's half-norms: no CTA barrier
+      // Fused top-KC over t = -(score): bigger is better.  Lists keep scores (ascending, best first).
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const tc_item item = items[it];
         float lv[KC > 0 ? KC : 1];
@@ -249,14 +252,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const float bv      = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
           thr0                = (bv - b_add) / bound.scale;
         }
-        float thr = thr0;
-        int cnt   = 0;
+        float thr_t = -thr0;  // an element is a candidate iff t > thr_t
+        int cnt     = 0;
+        const int kth = (bound.kth > 0 && bound.kth < KC) ? bound.kth : KC;
+        // lv[kth - 1] without a dynamically indexed (= local-memory) array: the list is sorted ascending
+        auto kth_best = [&]() {
+          float v = lv[0];
+#pragma unroll
+          for (int j = 1; j < KC; ++j) v = fmaxf(v, j < kth ? lv[j] : -INFINITY);
+          return v;
+        };
 
         auto flush = [&]() {
           for (int e = 0; e < cnt; ++e) {
             const uint2 en   = qe[e * kEpiThreads + et];
-            const float s    = __uint_as_float(en.x);
-            const uint32_t p = en.y + (en.x & 15u);
+            const float s    = -__uint_as_float(en.x);
+            const uint32_t p = en.y;
             if (s < lv[KC - 1]) {
 #pragma unroll
               for (int j = KC - 1; j > 0; --j) {
@@ -266,64 +277,57 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (s < lv[0]) { lv[0] = s; li[0] = p; }
             }
           }
-          cnt = 0;
-          thr = fminf(thr0, lv[KC - 1]);
+          cnt   = 0;
+          thr_t = -fminf(thr0, kth_best());
         };
 
-        const float* hn_item = hn + item.b_row0 + col0;
-        // lanes 0..kCols/4-1 each stage one float4 of the warp's column range
-        float4 hn_reg = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + lane * 4);
-        for (uint32_t t = 0; t < item.n_tiles; ++t) {
-          if (lane < kCols / 4) *reinterpret_cast<float4*>(hn_w + acc * kCols + lane * 4) = hn_reg;
-          __syncwarp();
-          if (t + 1 < item.n_tiles && lane < kCols / 4) hn_reg = *reinterpret_cast<const float4*>(hn_item + (t + 1) * 128 + lane * 4);
-          ptx::mbar_wait(&tfull[acc], acc_phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t pos0 = item.b_row0 + t * 128 + col0;
-          if (!dbg_skip_epilogue) {
-#pragma unroll 1
-            for (int ch = 0; ch < kCols / 32; ++ch) {
-              uint32_t v[32];
-              ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128 + col0 + ch * 32, v);
-              ptx::tmem_ld_wait();
+        // 32 accumulator columns: max-tree per quad, one compare for the whole chunk; hits are rare
+        auto scan32 = [&](const uint32_t (&v)[32], uint32_t pos) {
+          if (__any_sync(0xffffffffu, cnt > kQueue / 2)) flush();
+          float qm[8];
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                if (__any_sync(0xffffffffu, cnt > kQueue - kChunk)) flush();
-                const float4* h4 = reinterpret_cast<const float4*>(hn_w + acc * kCols + ch * 32 + g * 16);
-                float sc[16];
+          for (int qd = 0; qd < 8; ++qd)
+            qm[qd] = fmaxf(fmaxf(__uint_as_float(v[qd * 4 + 0]), __uint_as_float(v[qd * 4 + 1])),
+                           fmaxf(__uint_as_float(v[qd * 4 + 2]), __uint_as_float(v[qd * 4 + 3])));
+          const float m = fmaxf(fmaxf(fmaxf(qm[0], qm[1]), fmaxf(qm[2], qm[3])), fmaxf(fmaxf(qm[4], qm[5]), fmaxf(qm[6], qm[7])));
+          if (m > thr_t) {
+            uint32_t pending = 0xffu;  // quads still to look at; a quad waits (and the lane flushes) when its queue is full
+            do {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  const float4 h = h4[c4];
-                  sc[c4 * 4 + 0] = __uint_as_float((__float_as_uint(h.x - __uint_as_float(v[g * 16 + c4 * 4 + 0])) & 0xfffffff0u) | (c4 * 4 + 0));
-                  sc[c4 * 4 + 1] = __uint_as_float((__float_as_uint(h.y - __uint_as_float(v[g * 16 + c4 * 4 + 1])) & 0xfffffff0u) | (c4 * 4 + 1));
-                  sc[c4 * 4 + 2] = __uint_as_float((__float_as_uint(h.z - __uint_as_float(v[g * 16 + c4 * 4 + 2])) & 0xfffffff0u) | (c4 * 4 + 2));
-                  sc[c4 * 4 + 3] = __uint_as_float((__float_as_uint(h.w - __uint_as_float(v[g * 16 + c4 * 4 + 3])) & 0xfffffff0u) | (c4 * 4 + 3));
-                }
-                const float q0 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
-                const float q1 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
-                const float q2 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
-                const float q3 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
-                const float mn = fminf(fminf(q0, q1), fminf(q2, q3));
-                if (mn < thr) {
-                  const uint32_t gbase = pos0 + ch * 32 + g * 16;
-                  uint2* qp = qe + cnt * kEpiThreads + et;
+              for (int qd = 0; qd < 8; ++qd) {
+                if ((pending >> qd) & 1u) {
+                  if (!(qm[qd] > thr_t)) {
+                    pending &= ~(1u << qd);
+                  } else if (cnt <= kQueue - 4) {
 #pragma unroll
-                  for (int c = 0; c < 16; ++c) {
-                    if (sc[c] < thr) { *qp = make_uint2(__float_as_uint(sc[c]), gbase); qp += kEpiThreads; ++cnt; }
+                    for (int e = 0; e < 4; ++e) {
+                      if (__uint_as_float(v[qd * 4 + e]) > thr_t) {
+                        qe[cnt * kEpiThreads + et] = make_uint2(v[qd * 4 + e], pos + qd * 4 + e);
+                        ++cnt;
+                      }
+                    }
+                    pending &= ~(1u << qd);
                   }
                 }
               }
-            }
+              if (pending) flush();
+            } while (pending);
           }
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&tempty[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+        };
+
+        for (uint32_t t = 0; t < item.n_tiles; ++t) {
+          uint32_t v0[32], v1[32];
+          fetch_tile(v0, v1);
+          if (!dbg_skip_epilogue) {
+            const uint32_t pos0 = item.b_row0 + t * 128 + col0;
+            scan32(v0, pos0);
+            scan32(v1, pos0 + 32);
+          }
         }
         flush();
-        if (b_key != nullptr && lv[KC - 1] < INFINITY) {
-          const float pub = b_add + bound.scale * lv[KC - 1];
+        const float my_kth = kth_best();
+        if (b_key != nullptr && my_kth < INFINITY) {
+          const float pub = b_add + bound.scale * my_kth;
           const int kp    = __float_as_int(pub);
           atomicMin(b_key, kp >= 0 ? kp : kp ^ 0x7fffffff);
         }
@@ -339,7 +343,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) { ptx::tmem_dealloc<256>(tmem_base); }
+  if (warp == 2) { ptx::tmem_dealloc<128 * kAccBufs>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -376,20 +380,38 @@ CUtensorMap make_plane_map(const __nv_bfloat16* ptr, int64_t rows, int Kp)
   return m;
 }
 
+// [rows, 16] bf16 half-norm extension plane, one 32-byte row per dataset row
+CUtensorMap make_ext_map(const __nv_bfloat16* ptr, int64_t rows)
+{
+  CUtensorMap m;
+  cuuint64_t gdim[2]    = {16, static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {16 * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2]     = {16, 128};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_EXPECTS(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (half-norm plane) failed with code %d (rows=%lld)", int(r), (long long)rows);
+  return m;
+}
+
 int env_int(const char* name, int dflt)
 {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
-template <int KB, int NPL, int KC, int EPIW>
+template <int KB, int NPL, int KC>
 void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-            const CUtensorMap& b_lo, const float* hn, const tc_item* items, int n_items, const int* n_items_dev,
+            const CUtensorMap& b_lo, const CUtensorMap& b_x, const tc_item* items, int n_items, const int* n_items_dev,
             float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound)
 {
-  auto kern = tc_scan_kernel<KB, NPL, KC, EPIW>;
-  using C   = cfg<KB, NPL, EPIW>;
-  static const int skip_epi = env_int("CUVS_B200_TC_SKIP_EPI", 0);  // profiling knob: MMA/TMA pipeline only
+  auto kern = tc_scan_kernel<KB, NPL, KC>;
+  using C   = cfg<KB, NPL>;
+  static_assert(C::smem <= 227 * 1024, "tc_scan_kernel: shared memory budget exceeded");
+  // profiling knob: MMA/TMA pipeline only (results are garbage); only honoured inside a timed region (cuvsB200TimingEnable)
+  static const int skip_env = env_int("CUVS_B200_TC_SKIP_EPI", 0);
+  const int skip_epi        = skip_env && timing_enabled() ? 1 : 0;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
@@ -398,7 +420,7 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
   int grid = n_items < sm_count ? n_items : sm_count;
   timed_section ts("tc_scan", stream);
   count_launch();
-  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, hn, items, n_items, n_items_dev, out_score, out_pos,
+  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, out_score, out_pos,
                                                out_row_stride, skip_epi, bound);
   B2_CUDA(cudaGetLastError());
 }
@@ -428,20 +450,48 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int64_t n, int6
   }
 }
 
-__global__ void half_norms_kernel(const float* __restrict__ xn, int64_t n, int64_t rows_pad, float* __restrict__ hn)
+// -hn as three bf16 pieces (exact: 3 x 8 significand bits) in columns 0..2 of a 16-wide row; +inf (padding) -> -inf
+__device__ __forceinline__ void store_ext_row(__nv_bfloat16* row, float hn)
+{
+  const float h = -hn;
+  __nv_bfloat16 p0, p1, p2;
+  if (isinf(h)) {
+    p0 = __float2bfloat16_rn(h);
+    p1 = p2 = __float2bfloat16_rn(0.f);
+  } else {
+    p0             = __float2bfloat16_rn(h);
+    const float r1 = h - __bfloat162float(p0);
+    p1             = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(p1);
+    p2             = __float2bfloat16_rn(r2);
+  }
+  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+  uint4 w0, w1 = make_uint4(0, 0, 0, 0);
+  __nv_bfloat162 a(p0, p1), b(p2, z);
+  w0.x = *reinterpret_cast<uint32_t*>(&a);
+  w0.y = *reinterpret_cast<uint32_t*>(&b);
+  w0.z = w0.w = 0;
+  reinterpret_cast<uint4*>(row)[0] = w0;
+  reinterpret_cast<uint4*>(row)[1] = w1;
+}
+
+__global__ void half_norms_kernel(const float* __restrict__ xn, int64_t n, int64_t rows_pad, __nv_bfloat16* __restrict__ hx)
 {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= rows_pad) return;
-  hn[i] = i < n ? (xn ? 0.5f * xn[i] : 0.0f) : INFINITY;
+  store_ext_row(hx + i * 16, i < n ? (xn ? 0.5f * xn[i] : 0.0f) : INFINITY);
+}
+
+__global__ void pack_half_norms_kernel(const float* __restrict__ hn, int64_t rows_pad, __nv_bfloat16* __restrict__ hx)
+{
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= rows_pad) return;
+  store_ext_row(hx + i * 16, hn[i]);
 }
 
 }  // namespace
 
-int tc_lists_per_item()
-{
-  static const int epiw = env_int("CUVS_B200_TC_EPIW", 8);
-  return epiw == 4 ? 1 : 2;
-}
+int tc_lists_per_item() { return 2; }
 
 bool tc_supported(int device, int d)
 {
@@ -461,17 +511,25 @@ void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld,
   B2_CUDA(cudaGetLastError());
 }
 
-void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn)
+void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, __nv_bfloat16* hx)
 {
   if (rows_pad == 0) return;
   count_launch();
-  half_norms_kernel<<<static_cast<unsigned>((rows_pad + 255) / 256), 256, 0, stream>>>(xn, n, rows_pad, hn);
+  half_norms_kernel<<<static_cast<unsigned>((rows_pad + 255) / 256), 256, 0, stream>>>(xn, n, rows_pad, hx);
+  B2_CUDA(cudaGetLastError());
+}
+
+void tc_pack_half_norms(cudaStream_t stream, const float* hn, int64_t rows_pad, __nv_bfloat16* hx)
+{
+  if (rows_pad == 0) return;
+  count_launch();
+  pack_half_norms_kernel<<<static_cast<unsigned>((rows_pad + 255) / 256), 256, 0, stream>>>(hn, rows_pad, hx);
   B2_CUDA(cudaGetLastError());
 }
 
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
-                  const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
+                  const __nv_bfloat16* hx, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
                   float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound)
 {
   if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
@@ -479,21 +537,18 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   B2_EXPECTS(KC == 0 || KC == 16 || KC == 32, "tc_scan_topk: KC must be 0 (store), 16 or 32");
   B2_EXPECTS(passes == 1 || passes == 3, "tc_scan_topk: passes must be 1 or 3");
   B2_EXPECTS(passes == 1 || (a_lo && b_lo), "tc_scan_topk: lo planes required for 3-pass mode");
-  const int sms  = sm_count_of(device);
-  const int epiw = tc_lists_per_item() * 4;
+  const int sms = sm_count_of(device);
   static const int no_bound = env_int("CUVS_B200_TC_NO_BOUND", 0);  // profiling knob
-  const tc_bound bnd = (bound && !no_bound) ? *bound : tc_bound{};
+  tc_bound bnd = bound ? *bound : tc_bound{};
+  if (no_bound) { bnd.keys = nullptr; }
   CUtensorMap mA  = make_plane_map(a_hi, a_rows_pad, Kp);
   CUtensorMap mB  = make_plane_map(b_hi, b_rows_pad, Kp);
   CUtensorMap mAl = passes == 3 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
   CUtensorMap mBl = passes == 3 ? make_plane_map(b_lo, b_rows_pad, Kp) : mB;
+  CUtensorMap mBx = make_ext_map(hx, b_rows_pad);
 #define B2_TC_CASE(KB_, NPL_, KC_)                                                                                     \
   if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
-  {                                                                                                                    \
-    if (epiw == 8)                                                                                                     \
-      return launch<KB_, NPL_, KC_, 8>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd); \
-    return launch<KB_, NPL_, KC_, 4>(stream, sms, mA, mAl, mB, mBl, hn, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd);   \
-  }
+    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd);
   B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 2, 0)
   B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 2, 0)
 #undef B2_TC_CASE

@@ -37,14 +37,16 @@ struct tc_bound {
   const uint32_t* idx = nullptr;  // [a_rows] bound slot of every A row (null: the A row itself)
   const float* add    = nullptr;  // [a_rows] (null: 0)
   float scale         = 1.0f;
+  int kth             = 0;        // the caller only needs each query's kth best (1..KC; 0 = KC): lists prune at, and publish,
+                                  // their kth entry instead of their last one
 };
 constexpr int tc_bound_init_byte = 0x7f;  // memset value: 0x7f7f7f7f decodes to 3.39e38
 
 inline int tc_pad_k(int d) { return (d + 63) / 64 * 64; }
 inline int64_t tc_pad_rows(int64_t n) { return (n + kTcTile - 1) / kTcTile * kTcTile; }
 
-/** Candidate lists the kernel emits per (item, query row): 1 or 2 (two epilogue warps per TMEM lane quarter,
- *  each owning half of the tile's columns).  Every list holds KC entries; list j sits at +j*KC. */
+/** Candidate lists the kernel emits per (item, query row): 2 (two epilogue warps per TMEM lane quarter, each owning
+ *  64 of the tile's 128 columns).  Every list holds KC entries; list j sits at +j*KC. */
 int tc_lists_per_item();
 
 /** True when the device/shape combination is served by the tcgen05 kernel (sm_100, Kp <= 128). */
@@ -57,8 +59,14 @@ bool tc_supported(int device, int d);
 void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld, int d, int Kp, __nv_bfloat16* hi,
                      __nv_bfloat16* lo, int64_t rows_pad, const float* row_scale);
 
-/** hn[j] = 0.5 * xn[j] (or 0 when xn == null) for j < n, +inf for n <= j < rows_pad. */
-void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, float* hn);
+/**
+ * Half-norm plane hx [rows_pad, 16] bf16 (32 bytes per row): columns 0..2 hold -hn[j] as three bf16 pieces (exact),
+ * hn[j] = 0.5 * xn[j] (or 0 when xn == null) for j < n, +inf for n <= j < rows_pad; columns 3..15 are zero.  The scan
+ * kernel feeds it to the tensor cores as one extra K = 16 step, so the accumulator is q.x - hn directly.
+ */
+void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows_pad, __nv_bfloat16* hx);
+/** Same plane from ready-made half norms hn[rows_pad] (may hold +inf for rows to exclude). */
+void tc_pack_half_norms(cudaStream_t stream, const float* hn, int64_t rows_pad, __nv_bfloat16* hx);
 
 /**
  * Run the scan.  For every item and every valid row r the kernel writes tc_lists_per_item() lists of KC
@@ -71,7 +79,7 @@ void tc_half_norms(cudaStream_t stream, const float* xn, int64_t n, int64_t rows
  */
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
-                  const float* hn, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
+                  const __nv_bfloat16* hx, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
                   float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound = nullptr);
 
 }  // namespace b200

@@ -85,7 +85,7 @@ def test_build_search_save_load(tmp_path):
     m = _mod()
     # embedding-like data (rank-8 manifold in 64-d): iid uniform points in 64-d have no neighbour structure to walk
     rng = np.random.default_rng(21)
-    A = rng.standard_normal((8, 64)).astype(np.float32) / np.sqrt(8)
+    A = (rng.standard_normal((8, 64)) / np.sqrt(8)).astype(np.float32)
     ds = (rng.standard_normal((20000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((20000, 64)).astype(np.float32))
     qs = (rng.standard_normal((300, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((300, 64)).astype(np.float32))
     index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
