@@ -41,6 +41,7 @@ constexpr int kAccBufs    = 4;          // TMEM accumulator ring
 constexpr int kEpiWarps   = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kCols       = 64;         // accumulator columns per epilogue thread and tile
+constexpr int kSched      = 4;          // depth of the work-item ring between the producer and its consumers
 
 template <int KB, int NPL>
 struct cfg {
@@ -48,9 +49,9 @@ struct cfg {
   static constexpr int stages      = NPL == 2 ? 3 : 6;
   static constexpr int a_bytes     = NPL * KB * kTileBytes;
   static constexpr int stage_bytes = NPL * kTileBytes + kExtBytes;  // ext slot used by the kb == 0 stage of a tile
-  static constexpr int n_bars      = 2 * stages + 2 + 2 * kAccBufs;
+  static constexpr int n_bars      = 2 * stages + 2 + 2 * kAccBufs + 2 * kSched;
   static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + kExtBytes /*ones*/ + stages * stage_bytes +
-                                 kQueue * kEpiThreads * 8 /*queues*/ + n_bars * 8 + 16;
+                                 kQueue * kEpiThreads * 8 /*queues*/ + n_bars * 8 + kSched * 4 + 16;
 };
 
 // KC > 0: fused top-KC epilogue, two candidate lists per (item, query row) — one per 64-column half of the tiles.
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(64 + kEpiThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_x, const tc_item* __restrict__ items, int n_items_host,
-               const int* __restrict__ n_items_dev, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
+               const int* __restrict__ n_items_dev, int* __restrict__ sched_counter, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
                int64_t out_row_stride, int dbg_skip_epilogue, tc_bound bound)
 {
   using C = cfg<KB, NPL>;
@@ -81,7 +82,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* a_empty = a_full + 1;
   uint64_t* tfull   = a_empty + 1;       // [kAccBufs]
   uint64_t* tempty  = tfull + kAccBufs;  // [kAccBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccBufs);
+  uint64_t* s_full  = tempty + kAccBufs;  // [kSched] work-item ring: producer -> MMA issuer + epilogue
+  uint64_t* s_empty = s_full + kSched;    // [kSched]
+  int* s_item       = reinterpret_cast<int*>(s_empty + kSched);  // [kSched] item index, -1 = no more work
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_item + kSched);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -105,6 +109,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], kEpiThreads);
     }
+    for (int s = 0; s < kSched; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&s_empty[s], 1 + kEpiThreads);
+    }
     ptx::fence_barrier_init();
   }
   // the constant A-side operand of the half-norm step: every row = {1, 1, 1, 0, 0, 0, 0, 0} in BOTH 16-byte chunks
@@ -121,8 +129,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      // Work items are handed out dynamically (one global counter): CTAs that finish early take the next item, and the
+      // items of one list — adjacent in the work list — are picked up at about the same time by different SMs, so the
+      // list's tiles are read from HBM once and from L2 by the others.
+      uint32_t stage = 0, phase = 0, a_phase = 0, ss = 0, sp = 0;
+      for (;;) {
+        ptx::mbar_wait(&s_empty[ss], sp ^ 1);
+        int it = atomicAdd(sched_counter, 1);
+        if (it >= n_items) it = -1;
+        s_item[ss] = it;
+        ptx::mbar_arrive(&s_full[ss]);
+        if (++ss == kSched) { ss = 0; sp ^= 1; }
+        if (it < 0) break;
         const tc_item item = items[it];
         ptx::mbar_wait(a_empty, a_phase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
@@ -154,8 +172,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
       const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
       const uint64_t ones   = ptx::make_smem_desc_sw32(ptx::smem_u32(sOnes));
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0, ss = 0, sp = 0;
+      for (;;) {
+        ptx::mbar_wait(&s_full[ss], sp);
+        const int it = s_item[ss];
+        ptx::mbar_arrive(&s_empty[ss]);
+        if (++ss == kSched) { ss = 0; sp ^= 1; }
+        if (it < 0) break;
         const uint32_t n_tiles = items[it].n_tiles;
         ptx::mbar_wait(a_full, a_phase);
         ptx::tc_fence_after_sync();
@@ -199,7 +222,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int et      = half * 128 + row;     // slot in the queue arrays
     const int col0    = half * kCols;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, ss = 0, sp = 0;
+    auto next_item = [&]() {
+      ptx::mbar_wait(&s_full[ss], sp);
+      const int it = s_item[ss];
+      ptx::mbar_arrive(&s_empty[ss]);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      return it;
+    };
 
     // One tile: wait for the accumulator, pull this thread's 64 columns into registers, hand the TMEM buffer back.
     auto fetch_tile = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
@@ -214,7 +244,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     };
 
     if constexpr (KC == 0) {
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int it = next_item(); it >= 0; it = next_item()) {
         const tc_item item = items[it];
         float* orow        = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride + col0;
         const bool live    = static_cast<uint32_t>(row) < item.valid_rows;
@@ -235,7 +265,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     } else {
       // Fused top-KC over t = -(score): bigger is better.  Lists keep scores (ascending, best first).
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int it = next_item(); it >= 0; it = next_item()) {
         const tc_item item = items[it];
         float lv[KC > 0 ? KC : 1];
         uint32_t li[KC > 0 ? KC : 1];
@@ -418,10 +448,12 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
     attr_set = true;
   }
   int grid = n_items < sm_count ? n_items : sm_count;
+  dbuf<int> sched(1, stream);  // the kernel's work-item counter
+  B2_CUDA(cudaMemsetAsync(sched.data(), 0, sizeof(int), stream));
   timed_section ts("tc_scan", stream);
   count_launch();
-  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, out_score, out_pos,
-                                               out_row_stride, skip_epi, bound);
+  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, sched.data(), out_score,
+                                               out_pos, out_row_stride, skip_epi, bound);
   B2_CUDA(cudaGetLastError());
 }
 
