@@ -263,7 +263,8 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
   tc_bound bnd;
   bnd.keys = bkeys.data();
   tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
-               idx.hx.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd);
+               idx.hx.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd,
+               false /*equal-sized items in split-major order: static round-robin keeps each column range L2 resident*/);
   if (row_stride > KC) {
     out.score.alloc(static_cast<size_t>(nq) * KC, stream);
     out.pos.alloc(static_cast<size_t>(nq) * KC, stream);

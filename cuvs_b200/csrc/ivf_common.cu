@@ -50,12 +50,12 @@ __global__ void first_of_rows_kernel(const uint32_t* __restrict__ pos, const flo
 // before any other item.  The per-query pruning bound (tc_bound) is therefore already tight — every query's closest
 // lists have been scanned — when the bulk of the work starts, and the epilogue's insert path is rarely taken.
 // Probes of empty lists (e.g. lists owned by another shard) are dropped here.
-__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int near_ranks,
+__global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int probe_ld, int near_ranks,
                                     const int64_t* __restrict__ list_offsets, uint32_t* __restrict__ counts)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
-  uint32_t l = probes[t];
+  uint32_t l = probes[(t / n_probes) * probe_ld + t % n_probes];
   if (l != 0xffffffffu && list_offsets[l + 1] > list_offsets[l])
     atomicAdd(&counts[2 * l + (static_cast<int>(t % n_probes) < near_ranks ? 0 : 1)], 1u);
 }
@@ -108,14 +108,14 @@ __global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __rest
   }
 }
 
-__global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int near_ranks,
+__global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64_t total, int n_probes, int probe_ld, int near_ranks,
                                       const int64_t* __restrict__ list_offsets, const uint32_t* __restrict__ pair_off,
                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_of,
                                       uint32_t* __restrict__ pair_query, uint32_t* __restrict__ pair_list)
 {
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
-  uint32_t l = probes[t];
+  uint32_t l = probes[(t / n_probes) * probe_ld + t % n_probes];
   if (l == 0xffffffffu || list_offsets[l + 1] <= list_offsets[l]) { slot_of[t] = 0xffffffffu; return; }
   const uint32_t b = 2 * l + (static_cast<int>(t % n_probes) < near_ranks ? 0 : 1);
   uint32_t slot    = pair_off[b] + atomicAdd(&cursor[b], 1u);
@@ -127,14 +127,14 @@ __global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64
 __global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ pair_off,
                                        const uint32_t* __restrict__ first_off, const uint32_t* __restrict__ rest_off,
                                        const int* __restrict__ n_items, const int64_t* __restrict__ list_offsets,
-                                       int64_t n_lists, int KC, tc_item* __restrict__ items)
+                                       int64_t n_lists, int KC, uint32_t max_tiles, tc_item* __restrict__ items)
 {
   int64_t l = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (l >= n_lists) return;
   uint32_t c = counts[2 * l] + counts[2 * l + 1];
   if (c == 0) return;
   const uint32_t b_row0  = static_cast<uint32_t>(list_offsets[l]);
-  const uint32_t n_tiles = static_cast<uint32_t>((list_offsets[l + 1] - list_offsets[l]) / 128);
+  const uint32_t n_tiles = min(max_tiles, static_cast<uint32_t>((list_offsets[l + 1] - list_offsets[l]) / 128));
   const uint32_t n_first = static_cast<uint32_t>(n_items[2]);
   uint32_t g = (c + 127) / 128;
   for (uint32_t j = 0; j < g; ++j) {
@@ -177,6 +177,81 @@ __global__ void gather_cands_kernel(const float* __restrict__ cs, const uint32_t
   }
   out_score[t] = s;
   out_pos[t]   = p;
+}
+
+// ---- per-query merge of the probes' candidate lists ------------------------------------------
+// One CTA per query.  The scan left, for every (query, probe) pair, KCW candidates (score, position) and — shared by all
+// pairs of the query — an upper bound B on the query's k-th best value (tc_bound).  Every candidate that can be among the k
+// best satisfies value <= B, and at least k candidates do (the list that published B), so: filter by B into shared memory
+// (typically a few dozen survivors out of n_probes * KCW), sort those, emit the k best.  Replaces a gather of all
+// candidates into a [nq, n_probes * KCW] matrix followed by a radix select over it.
+__device__ __forceinline__ uint32_t order_key(float f)
+{
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k)
+{
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(128)
+merge_pairs_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp, const uint32_t* __restrict__ slot_of,
+                   const float* __restrict__ add, float scale, const int* __restrict__ bound_keys, int n_probes, int KCW,
+                   int k, int cap, float* __restrict__ out_val, uint32_t* __restrict__ out_pos)
+{
+  extern __shared__ unsigned long long surv[];  // [cap] (order key << 32 | position)
+  __shared__ int count;
+  const int64_t q = blockIdx.x;
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  float bnd = INFINITY;
+  if (bound_keys) {
+    const int kb = bound_keys[q];
+    bnd          = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
+  }
+  const int total = n_probes * KCW;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int p         = e / KCW;
+    const int c         = e - p * KCW;
+    const uint32_t slot = slot_of[q * n_probes + p];
+    if (slot == 0xffffffffu) continue;
+    const uint32_t pos = cp[static_cast<int64_t>(slot) * KCW + c];
+    if (pos == 0xffffffffu) continue;
+    const float v = __fmaf_rn(scale, cs[static_cast<int64_t>(slot) * KCW + c], add ? add[slot] : 0.f);
+    if (v <= bnd) {
+      const int at = atomicAdd(&count, 1);
+      if (at < cap) surv[at] = (static_cast<unsigned long long>(order_key(v)) << 32) | pos;
+    }
+  }
+  __syncthreads();
+  const int n = min(count, cap);
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += blockDim.x) surv[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+        const int lo = (i / stride) * stride * 2 + (i % stride);
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = surv[lo], b = surv[hi];
+        if ((a > b) == up) { surv[lo] = b; surv[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    float v      = FLT_MAX;
+    uint32_t pos = 0xffffffffu;
+    if (j < n) {
+      v   = order_key_inv(static_cast<uint32_t>(surv[j] >> 32));
+      pos = static_cast<uint32_t>(surv[j] & 0xffffffffu);
+    }
+    out_val[q * k + j] = v;
+    out_pos[q * k + j] = pos;
+  }
 }
 
 // ---- k-means ---------------------------------------------------------------------------------
@@ -334,8 +409,9 @@ void assign_nearest(resources* res, const __nv_bfloat16* x_hi, const __nv_bfloat
 }
 
 void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_probes, int64_t n_lists,
-                   const int64_t* list_offsets_dev, int KC, probe_buckets& out)
+                   const int64_t* list_offsets_dev, int KC, probe_buckets& out, int probe_ld, uint32_t max_tiles)
 {
+  if (probe_ld <= 0) probe_ld = n_probes;
   auto s              = res->stream;
   const int64_t total = nq * n_probes;
   out.n_pairs         = total;
@@ -350,14 +426,14 @@ void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_pro
     first_off(static_cast<size_t>(n_lists), s), rest_off(static_cast<size_t>(n_lists), s), cursor(static_cast<size_t>(2 * n_lists), s);
   B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * 2 * n_lists, s));
   count_launch(4);
-  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, near_ranks, list_offsets_dev, counts.data());
+  count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, probe_ld, near_ranks, list_offsets_dev, counts.data());
   scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), first_off.data(), rest_off.data(), out.n_items.data(),
                                        cursor.data());
-  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, near_ranks, list_offsets_dev, pair_off.data(),
+  scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, probe_ld, near_ranks, list_offsets_dev, pair_off.data(),
                                                                 cursor.data(), out.slot_of.data(), out.pair_query.data(),
                                                                 out.pair_list.data());
   make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), first_off.data(), rest_off.data(),
-                                                                   out.n_items.data(), list_offsets_dev, n_lists, KC, out.items.data());
+                                                                   out.n_items.data(), list_offsets_dev, n_lists, KC, max_tiles, out.items.data());
   B2_CUDA(cudaGetLastError());
 }
 
@@ -379,6 +455,30 @@ void gather_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp
   count_launch();
   gather_cands_kernel<<<blocks_for(total, 256), 256, 0, s>>>(cs, cp, slot_of, total, KC, out_score, out_pos);
   B2_CUDA(cudaGetLastError());
+}
+
+bool merge_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp, const uint32_t* slot_of, const float* add,
+                            float scale, const int* bound_keys, int64_t nq, int n_probes, int KCW, int k, float* out_val,
+                            uint32_t* out_pos)
+{
+  const int64_t total = static_cast<int64_t>(n_probes) * KCW;
+  if (nq == 0) return true;
+  // without a bound every candidate survives the filter: only worth it while they all fit in shared memory
+  const int cap = static_cast<int>(std::min<int64_t>(total, 8192));
+  if (bound_keys == nullptr && total > cap) return false;
+  int cap2 = 1;
+  while (cap2 < cap) cap2 <<= 1;
+  const size_t smem = static_cast<size_t>(cap2) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    attr_set = true;
+  }
+  count_launch();
+  merge_pairs_kernel<<<static_cast<unsigned>(nq), 128, smem, s>>>(cs, cp, slot_of, add, scale, bound_keys, n_probes, KCW, k, cap,
+                                                                   out_val, out_pos);
+  B2_CUDA(cudaGetLastError());
+  return true;
 }
 
 void update_centers(cudaStream_t s, const float* x, int64_t n, int d, const uint32_t* labels, const float* weights, int k,

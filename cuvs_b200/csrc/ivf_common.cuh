@@ -64,7 +64,8 @@ struct probe_buckets {
 };
 void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_probes, int64_t n_lists,
                    const int64_t* list_offsets_dev /*[n_lists+1], padded row offsets (multiples of 128)*/, int KC,
-                   probe_buckets& out);
+                   probe_buckets& out, int probe_ld = 0 /*row stride of `probes` (0: n_probes)*/,
+                   uint32_t max_tiles = 0xffffffffu /*scan at most this many tiles of each list (bound warm-up)*/);
 
 /** Gather bf16 rows: dst[slot] = src[pair_query[slot]] (Kp elements each); rows >= *n_live are zeroed up to rows_total. */
 void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* pair_query, const int* n_live, int64_t rows_total,
@@ -73,6 +74,16 @@ void gather_rows_bf16(cudaStream_t s, const __nv_bfloat16* src, const uint32_t* 
 /** Per query, concatenate the KC candidates of each of its probes: out [nq, n_probes*KC]. */
 void gather_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp, const uint32_t* slot_of, int64_t nq,
                              int n_probes, int KC, float* out_score, uint32_t* out_pos);
+
+/**
+ * Per query: the k best (value, position) among its probes' candidates, value = add[slot] + scale * score, sorted
+ * ascending (ties: smaller position), missing entries (FLT_MAX, 0xffffffff).  `bound_keys` [nq] is the scan's tc_bound
+ * state — an upper bound on each query's k-th best value in the same units (null: no bound).  Returns false (nothing
+ * launched) when the shape needs the generic gather + select_k path instead.
+ */
+bool merge_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp, const uint32_t* slot_of, const float* add,
+                            float scale, const int* bound_keys, int64_t nq, int n_probes, int KCW, int k, float* out_val,
+                            uint32_t* out_pos);
 
 /**
  * Balanced-ish Lloyd k-means on the device (fp32 data, tcgen05 assignment).  `centers` [k, d] is

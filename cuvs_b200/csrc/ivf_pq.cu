@@ -790,6 +790,7 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   dbuf<float> cs(static_cast<size_t>(pb.n_pairs) * KCW, s);
   dbuf<uint32_t> cp(static_cast<size_t>(pb.n_pairs) * KCW, s);
   dbuf<float> add;
+  dbuf<int> bkeys;  // per-query pruning bound of the tensor-core scan (tc_bound), reused by the merge
   float scale = 1.0f;
 
   if (use_tc) {
@@ -805,8 +806,10 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
     scale = ip ? 1.0f : 2.0f;  // L2: |r|^2 + 2 (|y|^2/2 - r.y); IP: -(q.(c+y))
     {
       // probes of one query share a running bound on its k'-th best DISTANCE: d = add[slot] + scale * s
-      dbuf<int> bkeys(static_cast<size_t>(nq), s);
-      B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq, s));
+      if (k <= KC) {  // the bound tracks a k-th best out of KC kept entries
+        bkeys.alloc(static_cast<size_t>(nq), s);
+        B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq, s));
+      }
       tc_bound bnd;
       bnd.keys  = bkeys.data();
       bnd.idx   = pb.pair_query.data();
@@ -815,7 +818,7 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
       bnd.kth   = k;  // only the query's k best survive the merge below
       timed_section ts("pq_scan", s);
       tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
+                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
     }
   } else {
     const int book      = idx.book();
@@ -850,13 +853,17 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
 
   // ---- per query: concatenate its probes' candidates (already in final distance units), top-k, ids
   const int64_t cand_w = static_cast<int64_t>(n_probes) * KCW;
-  dbuf<float> gs(static_cast<size_t>(nq) * cand_w, s);
-  dbuf<uint32_t> gp(static_cast<size_t>(nq) * cand_w, s);
-  count_launch();
-  gather_pq_cands_kernel<<<blocks_for(nq * cand_w, 256), 256, 0, s>>>(cs.data(), cp.data(), pb.slot_of.data(), use_tc ? add.data() : nullptr,
-                                                                       scale, nq * cand_w, KCW, gs.data(), gp.data());
   dbuf<uint32_t> mp(static_cast<size_t>(nq) * k, s);
-  select_k(s, gs.data(), gp.data(), IDX_U32, nq, cand_w, cand_w, k, out_dist, mp.data(), IDX_U32, true);
+  if (!(bkeys.data() != nullptr &&
+        merge_probe_candidates(s, cs.data(), cp.data(), pb.slot_of.data(), add.data(), scale, bkeys.data(), nq, static_cast<int>(n_probes),
+                               KCW, k, out_dist, mp.data()))) {
+    dbuf<float> gs(static_cast<size_t>(nq) * cand_w, s);
+    dbuf<uint32_t> gp(static_cast<size_t>(nq) * cand_w, s);
+    count_launch();
+    gather_pq_cands_kernel<<<blocks_for(nq * cand_w, 256), 256, 0, s>>>(cs.data(), cp.data(), pb.slot_of.data(), use_tc ? add.data() : nullptr,
+                                                                         scale, nq * cand_w, KCW, gs.data(), gp.data());
+    select_k(s, gs.data(), gp.data(), IDX_U32, nq, cand_w, cand_w, k, out_dist, mp.data(), IDX_U32, true);
+  }
   count_launch();
   finish_ids_kernel<<<blocks_for(nq * k, 256), 256, 0, s>>>(mp.data(), idx.ids.data(), out_dist, nq * k, int(idx.metric), out_idx);
   B2_CUDA(cudaGetLastError());

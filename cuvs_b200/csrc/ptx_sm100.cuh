@@ -69,6 +69,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
   while (!mbar_try_wait(bar, parity)) {}
 }
 
+// experiment variants of the wait: no suspend-time hint (plain polling), or a caller-chosen hint
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  do {
+    asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns)
+{
+  uint32_t ok;
+  do {
+    asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  } while (!ok);
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m)
 {
@@ -81,6 +113,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
     ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
     : "memory");
+}
+// 2-D tile prefetch into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
 }
 // 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
@@ -119,6 +157,26 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uin
     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
     : "memory");
 }
+// Same, with the two shared-memory descriptors given as (lo, hi) 32-bit halves: consecutive K steps / stages differ only
+// in the low word (start address >> 4), so the issuing thread spends one integer add per operand and MMA.
+__device__ __forceinline__ void mma_bf16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t"
+    ".reg .pred p;\n\t"
+    ".reg .b64 da, db;\n\t"
+    "mov.b64 da, {%1, %2};\n\t"
+    "mov.b64 db, {%3, %4};\n\t"
+    "setp.ne.b32 p, %6, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+    "}\n"
+    ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3ffffu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSw32  = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO 256 B, version 1, SWIZZLE_32B
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
 {

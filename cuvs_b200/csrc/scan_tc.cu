@@ -41,6 +41,7 @@ constexpr int kAccBufs    = 4;          // TMEM accumulator ring
 constexpr int kEpiWarps   = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kCols       = 64;         // accumulator columns per epilogue thread and tile
+constexpr int kPrefetch   = 8;          // L2 prefetch distance of the B stream, in tiles
 constexpr int kSched      = 4;          // depth of the work-item ring between the producer and its consumers
 
 template <int KB, int NPL>
@@ -63,8 +64,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_x, const tc_item* __restrict__ items, int n_items_host,
                const int* __restrict__ n_items_dev, int* __restrict__ sched_counter, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
-               int64_t out_row_stride, int dbg_skip_epilogue, tc_bound bound)
+               int64_t out_row_stride, int dbg_flags, tc_bound bound)
 {
+  const int dbg_skip_epilogue = dbg_flags & 1;
+  const bool prefetch_on      = (dbg_flags & 2) == 0;
+  const uint32_t nst          = (dbg_flags >> 8) ? min(static_cast<uint32_t>(dbg_flags >> 8), static_cast<uint32_t>(cfg<KB, NPL>::stages)) : cfg<KB, NPL>::stages;  // ring depth (experiment knob)
   using C = cfg<KB, NPL>;
   const int n_items = n_items_dev ? *n_items_dev : n_items_host;
   // 1024-byte alignment is what SWIZZLE_128B operand tiles need; declared on the array (no integer
@@ -87,7 +91,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   int* s_item       = reinterpret_cast<int*>(s_empty + kSched);  // [kSched] item index, -1 = no more work
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_item + kSched);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform by construction (shuffle broadcast): lets the compiler keep role dispatch and the issue loops convergent
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA_hi);
@@ -107,11 +112,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     ptx::mbar_init(a_empty, 1);
     for (int s = 0; s < kAccBufs; ++s) {
       ptx::mbar_init(&tfull[s], 1);
-      ptx::mbar_init(&tempty[s], kEpiThreads);
+      ptx::mbar_init(&tempty[s], kEpiWarps);
     }
     for (int s = 0; s < kSched; ++s) {
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&s_empty[s], 1 + kEpiThreads);
+      ptx::mbar_init(&s_empty[s], 1 + kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -124,25 +129,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      // Work items are handed out dynamically (one global counter): CTAs that finish early take the next item, and the
-      // items of one list — adjacent in the work list — are picked up at about the same time by different SMs, so the
-      // list's tiles are read from HBM once and from L2 by the others.
-      uint32_t stage = 0, phase = 0, a_phase = 0, ss = 0, sp = 0;
-      for (;;) {
-        ptx::mbar_wait(&s_empty[ss], sp ^ 1);
-        int it = atomicAdd(sched_counter, 1);
+    // The whole warp runs the (warp-uniform) control flow, one elected lane issues: keeps the loop free of the
+    // per-instruction ELECT/branch sequences a single-lane branch would get.
+    // Work items are handed out dynamically (one global counter): CTAs that finish early take the next item, and the
+    // items of one list — adjacent in the work list — are picked up at about the same time by different SMs, so the
+    // list's tiles are read from HBM once and from L2 by the others.
+    uint32_t stage = 0, phase = 0, a_phase = 0, ss = 0, sp = 0;
+    int static_it = static_cast<int>(blockIdx.x);  // sched_counter == null: plain round-robin over the grid
+    for (;;) {
+      ptx::mbar_wait(&s_empty[ss], sp ^ 1);
+      int it = 0;
+      if (lane == 0) {
+        if (sched_counter != nullptr) {
+          it = atomicAdd(sched_counter, 1);
+        } else {
+          it = static_it;
+          static_it += static_cast<int>(gridDim.x);
+        }
         if (it >= n_items) it = -1;
         s_item[ss] = it;
         ptx::mbar_arrive(&s_full[ss]);
-        if (++ss == kSched) { ss = 0; sp ^= 1; }
-        if (it < 0) break;
-        const tc_item item = items[it];
-        ptx::mbar_wait(a_empty, a_phase ^ 1);
+      }
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      const tc_item item = items[it];
+      ptx::mbar_wait(a_empty, a_phase ^ 1);
+      if (lane == 0) {
         ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -150,69 +167,86 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (NPL == 2)
             ptx::tma_load_2d(sA + (1 * KB + kb) * kTileBytes, &tmA_lo, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
         }
-        a_phase ^= 1;
-        for (uint32_t t = 0; t < item.n_tiles; ++t) {
-          const int32_t brow = static_cast<int32_t>(item.b_row0 + t * 128);
+      }
+      a_phase ^= 1;
+      for (uint32_t t = 0; t < item.n_tiles; ++t) {
+        const int32_t brow = static_cast<int32_t>(item.b_row0 + t * 128);
+        if (prefetch_on && lane == 0 && t + kPrefetch < item.n_tiles) {
+          const int32_t prow = brow + kPrefetch * 128;
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::tma_prefetch_2d(&tmB_hi, kb * 64, prow);
+            if (NPL == 2) ptx::tma_prefetch_2d(&tmB_lo, kb * 64, prow);
+          }
+          ptx::tma_prefetch_2d(&tmB_x, 0, prow);
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          if (lane == 0) {
             ptx::mbar_arrive_expect_tx(&full[stage], NPL * kTileBytes + (kb == 0 ? kExtBytes : 0));
             uint8_t* dst = sB + stage * C::stage_bytes;
             ptx::tma_load_2d(dst, &tmB_hi, &full[stage], kb * 64, brow);
             if (NPL == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
             if (kb == 0) ptx::tma_load_2d(dst + NPL * kTileBytes, &tmB_x, &full[stage], 0, brow);
-            if (++stage == C::stages) { stage = 0; phase ^= 1; }
           }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
-      const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
-      const uint64_t ones   = ptx::make_smem_desc_sw32(ptx::smem_u32(sOnes));
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0, ss = 0, sp = 0;
-      for (;;) {
-        ptx::mbar_wait(&s_full[ss], sp);
-        const int it = s_item[ss];
-        ptx::mbar_arrive(&s_empty[ss]);
-        if (++ss == kSched) { ss = 0; sp ^= 1; }
-        if (it < 0) break;
-        const uint32_t n_tiles = items[it].n_tiles;
-        ptx::mbar_wait(a_full, a_phase);
+    // ------------------------------------------------------------------ MMA issuer (whole warp loops, lane 0 issues)
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+    const uint32_t a_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sA));
+    const uint32_t b_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sB));
+    const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_u32(sOnes));
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0, ss = 0, sp = 0;
+    uint32_t b_lo = b_lo0;  // descriptor low word of the current B stage
+    for (;;) {
+      ptx::mbar_wait(&s_full[ss], sp);
+      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);  // (also: every lane has read the slot before it is handed back)
+      if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      const uint32_t n_tiles = __shfl_sync(0xffffffffu, items[it].n_tiles, 0);
+      ptx::mbar_wait(a_full, a_phase);
+      ptx::tc_fence_after_sync();
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (dbg_flags & 32) ptx::mbar_wait_poll(&tempty[acc], acc_phase ^ 1);
+        else if (dbg_flags & 64) ptx::mbar_wait_hint(&tempty[acc], acc_phase ^ 1, 1000);
+        else ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
-        for (uint32_t t = 0; t < n_tiles; ++t) {
-          ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
-          ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + acc * 128;
+        const uint32_t d_tmem = tmem_base + acc * 128;
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&full[stage], phase);
-            ptx::tc_fence_after_sync();
-            const uint32_t bs = b_addr + stage * C::stage_bytes;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t a_hi = ptx::make_smem_desc_sw128(a_addr + (0 * KB + kb) * kTileBytes + k * 32);
-              const uint64_t b_hi = ptx::make_smem_desc_sw128(bs + k * 32);
-              ptx::mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              // +2 per K = 16 step (32 bytes >> 4); k-block kb / plane p of A sit (p * KB + kb) * 1024 further (16 KB >> 4)
+              const uint32_t ah = a_lo0 + (0 * KB + kb) * 1024 + k * 2;
+              const uint32_t bh = b_lo + k * 2;
+              ptx::mma_bf16_ss_lohi(d_tmem, ah, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
               if (NPL == 2) {
-                const uint64_t a_lo = ptx::make_smem_desc_sw128(a_addr + (1 * KB + kb) * kTileBytes + k * 32);
-                const uint64_t b_lo = ptx::make_smem_desc_sw128(bs + kTileBytes + k * 32);
-                ptx::mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
-                ptx::mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                const uint32_t al = a_lo0 + (1 * KB + kb) * 1024 + k * 2;
+                const uint32_t bl = bh + 1024;
+                ptx::mma_bf16_ss_lohi(d_tmem, al, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, 1u);
+                ptx::mma_bf16_ss_lohi(d_tmem, ah, ptx::kDescHiSw128, bl, ptx::kDescHiSw128, idesc, 1u);
               }
             }
-            if (kb == 0) ptx::mma_bf16_ss(d_tmem, ones, ptx::make_smem_desc_sw32(bs + NPL * kTileBytes), idesc, 1u);  // -= |x|^2/2
+            if (kb == 0)  // -= |x|^2/2
+              ptx::mma_bf16_ss_lohi(d_tmem, ones_lo, ptx::kDescHiSw32, b_lo + NPL * 1024, ptx::kDescHiSw32, idesc, 1u);
             ptx::mma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
-            if (++stage == C::stages) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-          if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
+          b_lo += C::stage_bytes >> 4;
+          if (++stage == nst) { stage = 0; phase ^= 1; b_lo = b_lo0; }
         }
-        ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
-        a_phase ^= 1;
+        if (ptx::elect_one()) ptx::mma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
+      if (ptx::elect_one()) ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
+      a_phase ^= 1;
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps, 1 row x 64 columns per thread)
@@ -226,20 +260,26 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     auto next_item = [&]() {
       ptx::mbar_wait(&s_full[ss], sp);
       const int it = s_item[ss];
-      ptx::mbar_arrive(&s_empty[ss]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       return it;
     };
 
     // One tile: wait for the accumulator, pull this thread's 64 columns into registers, hand the TMEM buffer back.
     auto fetch_tile = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
-      ptx::mbar_wait(&tfull[acc], acc_phase);
+      if (dbg_flags & 16) ptx::mbar_wait_poll(&tfull[acc], acc_phase);
+      else if (dbg_flags & 64) ptx::mbar_wait_hint(&tfull[acc], acc_phase, 1000);
+      else ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after_sync();
       ptx::tmem_ld_32x32(t_lane + acc * 128, v0);
       ptx::tmem_ld_32x32(t_lane + acc * 128 + 32, v1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&tempty[acc]);
+      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise (~1000+ cycles per tile, more than a
+      // one-pass tile's MMAs)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
       if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
     };
 
@@ -282,6 +322,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const float bv      = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
           thr0                = (bv - b_add) / bound.scale;
         }
+        const bool live_row = static_cast<uint32_t>(row) < item.valid_rows;
+        if (!live_row) thr0 = -INFINITY;  // rows past the item's queries never collect candidates
         float thr_t = -thr0;  // an element is a candidate iff t > thr_t
         int cnt     = 0;
         const int kth = (bound.kth > 0 && bound.kth < KC) ? bound.kth : KC;
@@ -357,11 +399,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         flush();
         const float my_kth = kth_best();
         if (b_key != nullptr && my_kth < INFINITY) {
-          const float pub = b_add + bound.scale * my_kth;
+          const float pub = __fmaf_rn(bound.scale, my_kth, b_add);  // same expression as the consumers of the bound
           const int kp    = __float_as_int(pub);
           atomicMin(b_key, kp >= 0 ? kp : kp ^ 0x7fffffff);
         }
-        if (static_cast<uint32_t>(row) < item.valid_rows) {
+        if (live_row && out_score != nullptr) {
           float* os    = out_score + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
           uint32_t* op = out_pos + item.out_off + static_cast<int64_t>(row) * out_row_stride + half * KC;
 #pragma unroll
@@ -434,22 +476,26 @@ int env_int(const char* name, int dflt)
 template <int KB, int NPL, int KC>
 void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
             const CUtensorMap& b_lo, const CUtensorMap& b_x, const tc_item* items, int n_items, const int* n_items_dev,
-            float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound)
+            float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound, bool dynamic)
 {
   auto kern = tc_scan_kernel<KB, NPL, KC>;
   using C   = cfg<KB, NPL>;
   static_assert(C::smem <= 227 * 1024, "tc_scan_kernel: shared memory budget exceeded");
   // profiling knob: MMA/TMA pipeline only (results are garbage); only honoured inside a timed region (cuvsB200TimingEnable)
   static const int skip_env = env_int("CUVS_B200_TC_SKIP_EPI", 0);
-  const int skip_epi        = skip_env && timing_enabled() ? 1 : 0;
+  static const int no_pf    = env_int("CUVS_B200_TC_PREFETCH", 0) ? 0 : 1;  // L2 prefetch of the B stream: measured no gain, off
+  const int skip_epi        = (skip_env && timing_enabled() ? (skip_env & 0xf71) : 0) | (no_pf ? 2 : 0);  // 1 skip scan, 4 skip LDTM, 8 x64 LDTM
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
     attr_set = true;
   }
   int grid = n_items < sm_count ? n_items : sm_count;
-  dbuf<int> sched(1, stream);  // the kernel's work-item counter
-  B2_CUDA(cudaMemsetAsync(sched.data(), 0, sizeof(int), stream));
+  dbuf<int> sched;  // the kernel's work-item counter
+  if (dynamic) {
+    sched.alloc(1, stream);
+    B2_CUDA(cudaMemsetAsync(sched.data(), 0, sizeof(int), stream));
+  }
   timed_section ts("tc_scan", stream);
   count_launch();
   kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, sched.data(), out_score,
@@ -562,7 +608,7 @@ void tc_pack_half_norms(cudaStream_t stream, const float* hn, int64_t rows_pad, 
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
                   const __nv_bfloat16* hx, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
-                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound)
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound, bool dynamic_schedule)
 {
   if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
   B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
@@ -580,7 +626,7 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   CUtensorMap mBx = make_ext_map(hx, b_rows_pad);
 #define B2_TC_CASE(KB_, NPL_, KC_)                                                                                     \
   if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
-    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd);
+    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd, dynamic_schedule);
   B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 2, 0)
   B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 2, 0)
 #undef B2_TC_CASE

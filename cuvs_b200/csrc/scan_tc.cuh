@@ -74,12 +74,16 @@ void tc_pack_half_norms(cudaStream_t stream, const float* hn, int64_t rows_pad, 
  * (+inf, 0xffffffff).  `passes` = 3 uses hi*hi + lo*hi + hi*lo (fp32-grade products), 1 uses hi*hi.
  * KC must be 16 or 32 — or 0 for the dense "store" epilogue: all scores of the item are written to
  * out_score[out_off + r * out_row_stride + j], j = column offset inside the item's row range (out_pos unused).
+ * With KC > 0 and out_score == null nothing is written (a bound warm-up pass: only `bound` is updated).
+ * `dynamic_schedule`: items are handed to CTAs through a global counter (adjacent items — e.g. the query groups of one
+ * IVF list — run at the same time on different SMs and share the list's tiles through L2); false = static round-robin.
  * `n_items` is the host-known count or an upper bound; when `n_items_dev` is non-null the kernel reads the
  * exact count from it (work lists built on the device, no host round trip).
  */
 void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                   int64_t a_rows_pad, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int64_t b_rows_pad, int Kp,
                   const __nv_bfloat16* hx, const tc_item* items_dev, int n_items, const int* n_items_dev, int KC, int passes,
-                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound = nullptr);
+                  float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound = nullptr,
+                  bool dynamic_schedule = true);
 
 }  // namespace b200

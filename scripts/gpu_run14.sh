@@ -1,0 +1,24 @@
+#!/bin/bash
+mkdir -p gpurun_out
+R=gpurun_out/r14
+echo "== tests" > ${R}_tests.log
+timeout 1800 python -m pytest tests -m gpu -q -x --timeout=600 >> ${R}_tests.log 2>&1
+tail -n 5 ${R}_tests.log | cut -c1-300
+echo "== ivf_pq" > ${R}_bench.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu >> ${R}_bench.log 2>&1
+echo "== ivf_pq no warmup" >> ${R}_bench.log
+CUVS_B200_NO_WARMUP=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu >> ${R}_bench.log 2>&1
+echo "== brute_force" >> ${R}_bench.log
+timeout 900 python bench.py --workload brute_force --steps 10 --warmup 3 --no-cpu >> ${R}_bench.log 2>&1
+CUVS_B200_PROFILE=1 timeout 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
+  -k regex:tc_scan -c 3 -o ${R}_ivfpq_tc_scan python bench.py --steps 1 --warmup 3 --no-cpu > ${R}_ncu_full.log 2>&1
+python - <<'PY'
+import json
+for line in open('gpurun_out/r14_bench.log'):
+    line=line.strip()
+    if line.startswith('=='): print(line); continue
+    if line.startswith('{'):
+        j=json.loads(line)
+        print(' value %.0f e2e %.0f ms/step %.3f kernel_ms %.3f frac %.3f parity %s recall %s build %s' % (j['value'], j['e2e']['value'], j['ms_per_step'], j['roofline']['kernel_ms'], j['roofline']['frac'], j['parity_spot_check'], j['config'].get('recall_at_10'), j['config'].get('index_build_s')))
+    elif 'Error' in line or 'error' in line: print('  ', line[:300])
+PY
