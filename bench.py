@@ -189,7 +189,7 @@ class IvfPqWorkload:
     timing_section = "pq_scan"
 
     def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=1024, pq_dim=64, n_probes=64, refine_ratio=2, seed=1234,
-                 rank=0, world=1):
+                 rank=0, world=1, lut_dtype="f16"):
         from cuvs_b200.neighbors import brute_force, ivf_pq, refine
         self.n, self.d, self.nq, self.k = n, d, nq, k
         self.rank, self.world = rank, world
@@ -208,7 +208,10 @@ class IvfPqWorkload:
             self.index, self.sharded = self._build_shard(params)
         torch.cuda.synchronize()
         self.build_s = time.time() - t0
-        self.sp = ivf_pq.SearchParams(n_probes=n_probes)
+        import numpy as _np
+        self.lut_dtype = lut_dtype
+        lut = {"f32": _np.float32, "f16": _np.float16, "u8": _np.uint8}[lut_dtype]
+        self.sp = ivf_pq.SearchParams(n_probes=n_probes, lut_dtype=lut)
         self.kc = k * refine_ratio
         self.cand = torch.empty((nq, self.kc), dtype=torch.int64, device="cuda")
         self.cand_d = torch.empty((nq, self.kc), dtype=torch.float32, device="cuda")
@@ -294,7 +297,10 @@ class IvfPqWorkload:
         sizes = self.index.list_sizes.float()
         return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
                 "n_lists": self.n_lists, "pq_dim": self.pq_dim, "pq_bits": 8, "n_probes": self.n_probes,
-                "refine_ratio": self.refine_ratio, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "refine_ratio": self.refine_ratio, "lut_dtype": self.lut_dtype,
+                "scan": ("2-pass split-bf16 residual x bf16-exact decoded rows = the fp32 LUT sums to fp32 rounding" if self.lut_dtype == "f32"
+                         else "1-pass bf16 residual x decoded rows (reduced-precision LUT requested)"),
+                "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
                 "list_size_max_over_mean": round((sizes.max() / sizes.mean()).item(), 2),
                 "data": "rank-16 gaussian manifold in 128-d + 0.05 noise (embedding-like), seeds 1234/4321",
                 "l2_flush": "256 MiB write between timed steps",
@@ -468,6 +474,7 @@ def run_ours(args):
     if args.nq:
         kw["nq"] = args.nq
     if args.workload == "ivf_pq":
+        kw["lut_dtype"] = args.lut_dtype
         for name in ("n_lists", "n_probes", "refine_ratio", "pq_dim"):
             if getattr(args, name):
                 kw[name] = getattr(args, name)
@@ -619,6 +626,8 @@ def main():
     ap.add_argument("--n-probes", dest="n_probes", type=int, default=0)
     ap.add_argument("--refine-ratio", dest="refine_ratio", type=int, default=0)
     ap.add_argument("--pq-dim", dest="pq_dim", type=int, default=0)
+    ap.add_argument("--lut-dtype", dest="lut_dtype", default="f16", choices=["f32", "f16", "u8"],
+                    help="ivf_pq search lut_dtype: f16/u8 (reduced-precision LUT, the usual throughput setting) -> 1-pass bf16 scan; f32 (API default) -> 2-pass scan")
     ap.add_argument("--itopk", type=int, default=0)
     ap.add_argument("--degree", type=int, default=0)
     args = ap.parse_args()

@@ -195,12 +195,16 @@ __device__ __forceinline__ float order_key_inv(uint32_t k)
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kMergeThreads = 256;
+constexpr int kMergeCap     = 1024;
+
+__global__ void __launch_bounds__(kMergeThreads)
 merge_pairs_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp, const uint32_t* __restrict__ slot_of,
                    const float* __restrict__ add, float scale, const int* __restrict__ bound_keys, int n_probes, int KCW,
-                   int k, int cap, float* __restrict__ out_val, uint32_t* __restrict__ out_pos)
+                   int k, float* __restrict__ out_val, uint32_t* __restrict__ out_pos)
 {
-  extern __shared__ unsigned long long surv[];  // [cap] (order key << 32 | position)
+  __shared__ unsigned long long surv[kMergeCap];  // (order key << 32 | position)
+  __shared__ unsigned long long red[kMergeThreads / 32];
   __shared__ int count;
   const int64_t q = blockIdx.x;
   if (threadIdx.x == 0) count = 0;
@@ -210,47 +214,113 @@ merge_pairs_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp
     const int kb = bound_keys[q];
     bnd          = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
   }
-  const int total = n_probes * KCW;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  const int total          = n_probes * KCW;
+  const uint32_t* my_slots = slot_of + q * n_probes;
+  auto value_of = [&](int e, uint32_t& pos) -> float {  // candidate e of this query (FLT_MAX / 0xffffffff when empty)
     const int p         = e / KCW;
     const int c         = e - p * KCW;
-    const uint32_t slot = slot_of[q * n_probes + p];
-    if (slot == 0xffffffffu) continue;
-    const uint32_t pos = cp[static_cast<int64_t>(slot) * KCW + c];
-    if (pos == 0xffffffffu) continue;
-    const float v = __fmaf_rn(scale, cs[static_cast<int64_t>(slot) * KCW + c], add ? add[slot] : 0.f);
-    if (v <= bnd) {
-      const int at = atomicAdd(&count, 1);
-      if (at < cap) surv[at] = (static_cast<unsigned long long>(order_key(v)) << 32) | pos;
+    const uint32_t slot = my_slots[p];
+    pos                 = 0xffffffffu;
+    if (slot == 0xffffffffu) return FLT_MAX;
+    pos = cp[static_cast<int64_t>(slot) * KCW + c];
+    if (pos == 0xffffffffu) return FLT_MAX;
+    return __fmaf_rn(scale, cs[static_cast<int64_t>(slot) * KCW + c], add ? add[slot] : 0.f);
+  };
+  // filter: four independent candidates per thread and trip keep the dependent slot -> position/score loads overlapped
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMergeThreads) {
+    uint32_t slot[4], pos[4];
+    float sc[4], ad[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kMergeThreads;
+      slot[u]     = e < total ? my_slots[e / KCW] : 0xffffffffu;
     }
-  }
-  __syncthreads();
-  const int n = min(count, cap);
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  for (int i = n + threadIdx.x; i < n2; i += blockDim.x) surv[i] = ~0ull;
-  __syncthreads();
-  for (int size = 2; size <= n2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
-        const int lo = (i / stride) * stride * 2 + (i % stride);
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const unsigned long long a = surv[lo], b = surv[hi];
-        if ((a > b) == up) { surv[lo] = b; surv[hi] = a; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kMergeThreads;
+      const int c = e % KCW;
+      pos[u] = 0xffffffffu; sc[u] = 0.f; ad[u] = 0.f;
+      if (slot[u] != 0xffffffffu) {
+        pos[u] = cp[static_cast<int64_t>(slot[u]) * KCW + c];
+        sc[u]  = cs[static_cast<int64_t>(slot[u]) * KCW + c];
+        ad[u]  = add ? add[slot[u]] : 0.f;
       }
-      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pos[u] == 0xffffffffu) continue;
+      const float v = __fmaf_rn(scale, sc[u], ad[u]);
+      if (v <= bnd) {
+        const int at = atomicAdd(&count, 1);
+        if (at < kMergeCap) surv[at] = (static_cast<unsigned long long>(order_key(v)) << 32) | pos[u];
+      }
     }
   }
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    float v      = FLT_MAX;
-    uint32_t pos = 0xffffffffu;
-    if (j < n) {
-      v   = order_key_inv(static_cast<uint32_t>(surv[j] >> 32));
-      pos = static_cast<uint32_t>(surv[j] & 0xffffffffu);
+  __syncthreads();
+  const int n = count;
+  if (n <= kMergeCap) {
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + threadIdx.x; i < n2; i += blockDim.x) surv[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+          const int lo = (i / stride) * stride * 2 + (i % stride);
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const unsigned long long a = surv[lo], b = surv[hi];
+          if ((a > b) == up) { surv[lo] = b; surv[hi] = a; }
+        }
+        __syncthreads();
+      }
     }
-    out_val[q * k + j] = v;
-    out_pos[q * k + j] = pos;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      float v      = FLT_MAX;
+      uint32_t pos = 0xffffffffu;
+      if (j < n) {
+        v   = order_key_inv(static_cast<uint32_t>(surv[j] >> 32));
+        pos = static_cast<uint32_t>(surv[j] & 0xffffffffu);
+      }
+      out_val[q * k + j] = v;
+      out_pos[q * k + j] = pos;
+    }
+    return;
+  }
+  // More survivors than the buffer holds (no usable bound, or massive ties at it): k rounds of "smallest key above the
+  // previous one" over all candidates.  Slow, but only for the rare query that gets here.
+  unsigned long long last = 0;
+  bool first = true;
+  for (int j = 0; j < k; ++j) {
+    unsigned long long best = ~0ull;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      uint32_t pos;
+      const float v = value_of(e, pos);
+      if (pos == 0xffffffffu) continue;
+      const unsigned long long key = (static_cast<unsigned long long>(order_key(v)) << 32) | pos;
+      if ((first || key > last) && key < best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    best = red[0];
+    for (int w = 1; w < kMergeThreads / 32; ++w) best = red[w] < best ? red[w] : best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const bool have    = best != ~0ull;
+      out_val[q * k + j] = have ? order_key_inv(static_cast<uint32_t>(best >> 32)) : FLT_MAX;
+      out_pos[q * k + j] = have ? static_cast<uint32_t>(best & 0xffffffffu) : 0xffffffffu;
+    }
+    if (best == ~0ull) {  // exhausted: fill the rest
+      for (int r = j + 1 + threadIdx.x; r < k; r += blockDim.x) { out_val[q * k + r] = FLT_MAX; out_pos[q * k + r] = 0xffffffffu; }
+      return;
+    }
+    last  = best;
+    first = false;
   }
 }
 
@@ -461,22 +531,12 @@ bool merge_probe_candidates(cudaStream_t s, const float* cs, const uint32_t* cp,
                             float scale, const int* bound_keys, int64_t nq, int n_probes, int KCW, int k, float* out_val,
                             uint32_t* out_pos)
 {
-  const int64_t total = static_cast<int64_t>(n_probes) * KCW;
   if (nq == 0) return true;
-  // without a bound every candidate survives the filter: only worth it while they all fit in shared memory
-  const int cap = static_cast<int>(std::min<int64_t>(total, 8192));
-  if (bound_keys == nullptr && total > cap) return false;
-  int cap2 = 1;
-  while (cap2 < cap) cap2 <<= 1;
-  const size_t smem = static_cast<size_t>(cap2) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    attr_set = true;
-  }
+  // without a bound nothing is filtered: the generic gather + radix select is the better tool then
+  if (bound_keys == nullptr && static_cast<int64_t>(n_probes) * KCW > kMergeCap) return false;
   count_launch();
-  merge_pairs_kernel<<<static_cast<unsigned>(nq), 128, smem, s>>>(cs, cp, slot_of, add, scale, bound_keys, n_probes, KCW, k, cap,
-                                                                   out_val, out_pos);
+  merge_pairs_kernel<<<static_cast<unsigned>(nq), kMergeThreads, 0, s>>>(cs, cp, slot_of, add, scale, bound_keys, n_probes, KCW, k,
+                                                                          out_val, out_pos);
   B2_CUDA(cudaGetLastError());
   return true;
 }

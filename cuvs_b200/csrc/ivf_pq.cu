@@ -738,14 +738,11 @@ ivf_pq_index* ivf_pq_build(resources* res, const cuvsIvfPqIndexParams& p, const 
   return idx.release();
 }
 
-int env_path()
+int env_path()  // read on every search: tests switch paths inside one process
 {
-  static const int v = [] {
-    const char* e = getenv("CUVS_B200_PQ_PATH");
-    if (!e) return 0;
-    return strcmp(e, "lut") == 0 ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0);
-  }();
-  return v;
+  const char* e = getenv("CUVS_B200_PQ_PATH");
+  if (!e) return 0;
+  return strcmp(e, "lut") == 0 ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0);
 }
 
 void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearchParams& sp, const DLTensor& qt, const DLTensor& nt,
@@ -776,8 +773,14 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   rotate_rows(s, q, nq, idx.dim, idx.rotation.data(), idx.rot_dim, q_rot.data());
 
   // ---- bucket pairs by list
-  const bool want_tc = sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F && idx.yhat.data() != nullptr;
-  const bool use_tc  = env_path() == 1 ? false : (env_path() == 2 ? idx.yhat.data() != nullptr : want_tc);
+  // Decoded-row tensor-core scan whenever the index keeps decoded rows.  fp32 LUT + fp32 accumulation (the reference's
+  // exact formulation) -> 2-pass scan: the residual is split into two bf16 planes, the decoded rows ARE bf16, so the scores
+  // equal the LUT sums to fp32 rounding.  A reduced-precision LUT / accumulator request (fp16, fp8) -> 1-pass scan with the
+  // residual rounded to bf16: the same class of approximation, at tensor-core speed.  CUVS_B200_PQ_PATH=lut forces the
+  // faithful LUT kernel (bit-level emulation of the fp16 / fp_8bit<5> LUT entries).
+  const bool reduced = !(sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F);
+  const bool use_tc  = env_path() == 1 ? false : idx.yhat.data() != nullptr;
+  const int passes   = reduced ? 1 : 2;
   const int lists = use_tc ? tc_lists_per_item() : 1;
   // candidates kept per (query, probe): the tensor-core epilogue keeps `lists` sorted lists of KC (one per column half of
   // the tile); for k > KC the union of the two half lists stands in for the pair's top-k (exact whenever no more than KC of
@@ -795,13 +798,14 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
 
   if (use_tc) {
     const int64_t a_rows = pb.n_pairs + 128;
-    dbuf<__nv_bfloat16> a_hi(static_cast<size_t>(a_rows) * idx.Kp, s);
+    dbuf<__nv_bfloat16> a_hi(static_cast<size_t>(a_rows) * idx.Kp, s), a_lo;
+    if (passes == 2) a_lo.alloc(static_cast<size_t>(a_rows) * idx.Kp, s);
     add.alloc(static_cast<size_t>(pb.n_pairs), s);
     // slots that were dropped (empty lists) are never read; slots beyond the live pairs are zero rows
     count_launch();
     pair_rows_kernel<<<blocks_for(a_rows * 32, 256), 256, 0, s>>>(q_rot.data(), idx.centers_rot.data(), pb.pair_query.data(),
                                                                    pb.pair_list.data(), pb.n_items.data() + 1, a_rows, idx.rot_dim, idx.Kp, ip,
-                                                                   a_hi.data(), nullptr, add.data());
+                                                                   a_hi.data(), a_lo.data(), add.data());
     B2_CUDA(cudaGetLastError());
     scale = ip ? 1.0f : 2.0f;  // L2: |r|^2 + 2 (|y|^2/2 - r.y); IP: -(q.(c+y))
     {
@@ -817,8 +821,8 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
       bnd.scale = scale;
       bnd.kth   = k;  // only the query's k best survive the merge below
       timed_section ts("pq_scan", s);
-      tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
+      tc_scan_topk(s, res->device, a_hi.data(), a_lo.data(), a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
+                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, passes, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
     }
   } else {
     const int book      = idx.book();

@@ -44,12 +44,16 @@ constexpr int kCols       = 64;         // accumulator columns per epilogue thre
 constexpr int kPrefetch   = 8;          // L2 prefetch distance of the B stream, in tiles
 constexpr int kSched      = 4;          // depth of the work-item ring between the producer and its consumers
 
-template <int KB, int NPL>
+// PASSES: 1 = hi*hi; 2 = (hi + lo)*hi (exact A side: query rows at fp32 grade against bf16-exact B rows);
+//         3 = hi*hi + lo*hi + hi*lo (both sides split)
+template <int KB, int PASSES>
 struct cfg {
+  static constexpr int NA = PASSES >= 2 ? 2 : 1;  // A planes resident in shared memory
+  static constexpr int NB = PASSES == 3 ? 2 : 1;  // B planes streamed
   static constexpr int threads     = 64 + kEpiThreads;
-  static constexpr int stages      = NPL == 2 ? 3 : 6;
-  static constexpr int a_bytes     = NPL * KB * kTileBytes;
-  static constexpr int stage_bytes = NPL * kTileBytes + kExtBytes;  // ext slot used by the kb == 0 stage of a tile
+  static constexpr int stages      = NB == 2 ? 3 : (NA == 2 ? 5 : 6);
+  static constexpr int a_bytes     = NA * KB * kTileBytes;
+  static constexpr int stage_bytes = NB * kTileBytes + kExtBytes;  // ext slot used by the kb == 0 stage of a tile
   static constexpr int n_bars      = 2 * stages + 2 + 2 * kAccBufs + 2 * kSched;
   static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + kExtBytes /*ones*/ + stages * stage_bytes +
                                  kQueue * kEpiThreads * 8 /*queues*/ + n_bars * 8 + kSched * 4 + 16;
@@ -58,7 +62,7 @@ struct cfg {
 // KC > 0: fused top-KC epilogue, two candidate lists per (item, query row) — one per 64-column half of the tiles.
 // KC == 0: "store" epilogue — every score of the tile is written to
 // out_score[out_off + row * out_row_stride + (column within the item's range)] (dense distance block).
-template <int KB, int NPL, int KC>
+template <int KB, int PASSES, int KC>
 __global__ void __launch_bounds__(64 + kEpiThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -68,8 +72,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 {
   const int dbg_skip_epilogue = dbg_flags & 1;
   const bool prefetch_on      = (dbg_flags & 2) == 0;
-  const uint32_t nst          = (dbg_flags >> 8) ? min(static_cast<uint32_t>(dbg_flags >> 8), static_cast<uint32_t>(cfg<KB, NPL>::stages)) : cfg<KB, NPL>::stages;  // ring depth (experiment knob)
-  using C = cfg<KB, NPL>;
+  const uint32_t nst          = (dbg_flags >> 8) ? min(static_cast<uint32_t>(dbg_flags >> 8), static_cast<uint32_t>(cfg<KB, PASSES>::stages)) : cfg<KB, PASSES>::stages;  // ring depth (experiment knob)
+  using C = cfg<KB, PASSES>;
+  constexpr int NA = C::NA, NB = C::NB;
   const int n_items = n_items_dev ? *n_items_dev : n_items_host;
   // 1024-byte alignment is what SWIZZLE_128B operand tiles need; declared on the array (no integer
   // round-trip of the pointer) so that the compiler keeps every access in the shared address space.
@@ -98,10 +103,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     ptx::prefetch_tmap(&tmA_hi);
     ptx::prefetch_tmap(&tmB_hi);
     ptx::prefetch_tmap(&tmB_x);
-    if (NPL == 2) {
-      ptx::prefetch_tmap(&tmA_lo);
-      ptx::prefetch_tmap(&tmB_lo);
-    }
+    if (NA == 2) ptx::prefetch_tmap(&tmA_lo);
+    if (NB == 2) ptx::prefetch_tmap(&tmB_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::stages; ++s) {
@@ -157,14 +160,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       it = __shfl_sync(0xffffffffu, it, 0);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
-      const tc_item item = items[it];
+      tc_item item = items[it];
+      item.a_row0  = __shfl_sync(0xffffffffu, item.a_row0, 0);
+      item.b_row0  = __shfl_sync(0xffffffffu, item.b_row0, 0);
+      item.n_tiles = __shfl_sync(0xffffffffu, item.n_tiles, 0);
       ptx::mbar_wait(a_empty, a_phase ^ 1);
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           ptx::tma_load_2d(sA + (0 * KB + kb) * kTileBytes, &tmA_hi, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
-          if (NPL == 2)
+          if (NA == 2)
             ptx::tma_load_2d(sA + (1 * KB + kb) * kTileBytes, &tmA_lo, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
         }
       }
@@ -176,19 +182,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             ptx::tma_prefetch_2d(&tmB_hi, kb * 64, prow);
-            if (NPL == 2) ptx::tma_prefetch_2d(&tmB_lo, kb * 64, prow);
+            if (NB == 2) ptx::tma_prefetch_2d(&tmB_lo, kb * 64, prow);
           }
           ptx::tma_prefetch_2d(&tmB_x, 0, prow);
         }
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(&full[stage], NPL * kTileBytes + (kb == 0 ? kExtBytes : 0));
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&full[stage], NB * kTileBytes + (kb == 0 ? kExtBytes : 0));
             uint8_t* dst = sB + stage * C::stage_bytes;
             ptx::tma_load_2d(dst, &tmB_hi, &full[stage], kb * 64, brow);
-            if (NPL == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
-            if (kb == 0) ptx::tma_load_2d(dst + NPL * kTileBytes, &tmB_x, &full[stage], 0, brow);
+            if (NB == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
+            if (kb == 0) ptx::tma_load_2d(dst + NB * kTileBytes, &tmB_x, &full[stage], 0, brow);
           }
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
@@ -228,15 +234,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const uint32_t ah = a_lo0 + (0 * KB + kb) * 1024 + k * 2;
               const uint32_t bh = b_lo + k * 2;
               ptx::mma_bf16_ss_lohi(d_tmem, ah, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
-              if (NPL == 2) {
+              if (NA == 2) {
                 const uint32_t al = a_lo0 + (1 * KB + kb) * 1024 + k * 2;
-                const uint32_t bl = bh + 1024;
                 ptx::mma_bf16_ss_lohi(d_tmem, al, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, 1u);
+              }
+              if (NB == 2) {
+                const uint32_t bl = bh + 1024;
                 ptx::mma_bf16_ss_lohi(d_tmem, ah, ptx::kDescHiSw128, bl, ptx::kDescHiSw128, idesc, 1u);
               }
             }
             if (kb == 0)  // -= |x|^2/2
-              ptx::mma_bf16_ss_lohi(d_tmem, ones_lo, ptx::kDescHiSw32, b_lo + NPL * 1024, ptx::kDescHiSw32, idesc, 1u);
+              ptx::mma_bf16_ss_lohi(d_tmem, ones_lo, ptx::kDescHiSw32, b_lo + NB * 1024, ptx::kDescHiSw32, idesc, 1u);
             ptx::mma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
           }
           b_lo += C::stage_bytes >> 4;
@@ -473,13 +481,13 @@ int env_int(const char* name, int dflt)
   return v ? atoi(v) : dflt;
 }
 
-template <int KB, int NPL, int KC>
+template <int KB, int PASSES, int KC>
 void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
             const CUtensorMap& b_lo, const CUtensorMap& b_x, const tc_item* items, int n_items, const int* n_items_dev,
             float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound, bool dynamic)
 {
-  auto kern = tc_scan_kernel<KB, NPL, KC>;
-  using C   = cfg<KB, NPL>;
+  auto kern = tc_scan_kernel<KB, PASSES, KC>;
+  using C   = cfg<KB, PASSES>;
   static_assert(C::smem <= 227 * 1024, "tc_scan_kernel: shared memory budget exceeded");
   // profiling knob: MMA/TMA pipeline only (results are garbage); only honoured inside a timed region (cuvsB200TimingEnable)
   static const int skip_env = env_int("CUVS_B200_TC_SKIP_EPI", 0);
@@ -613,22 +621,24 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
   B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
   B2_EXPECTS(KC == 0 || KC == 16 || KC == 32, "tc_scan_topk: KC must be 0 (store), 16 or 32");
-  B2_EXPECTS(passes == 1 || passes == 3, "tc_scan_topk: passes must be 1 or 3");
-  B2_EXPECTS(passes == 1 || (a_lo && b_lo), "tc_scan_topk: lo planes required for 3-pass mode");
+  B2_EXPECTS(passes >= 1 && passes <= 3, "tc_scan_topk: passes must be 1, 2 or 3");
+  B2_EXPECTS(passes == 1 || a_lo, "tc_scan_topk: the A lo plane is required for 2- and 3-pass mode");
+  B2_EXPECTS(passes != 3 || b_lo, "tc_scan_topk: the B lo plane is required for 3-pass mode");
   const int sms = sm_count_of(device);
   static const int no_bound = env_int("CUVS_B200_TC_NO_BOUND", 0);  // profiling knob
   tc_bound bnd = bound ? *bound : tc_bound{};
   if (no_bound) { bnd.keys = nullptr; }
   CUtensorMap mA  = make_plane_map(a_hi, a_rows_pad, Kp);
   CUtensorMap mB  = make_plane_map(b_hi, b_rows_pad, Kp);
-  CUtensorMap mAl = passes == 3 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
+  CUtensorMap mAl = passes >= 2 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
   CUtensorMap mBl = passes == 3 ? make_plane_map(b_lo, b_rows_pad, Kp) : mB;
   CUtensorMap mBx = make_ext_map(hx, b_rows_pad);
-#define B2_TC_CASE(KB_, NPL_, KC_)                                                                                     \
-  if (Kp == 64 * KB_ && (passes == 3 ? 2 : 1) == NPL_ && KC == KC_)                                                    \
-    return launch<KB_, NPL_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd, dynamic_schedule);
-  B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 2, 0)
-  B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 2, 0)
+#define B2_TC_CASE(KB_, P_, KC_)                                                                                       \
+  if (Kp == 64 * KB_ && passes == P_ && KC == KC_)                                                                     \
+    return launch<KB_, P_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd, dynamic_schedule);
+  B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 3, 16) B2_TC_CASE(1, 3, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 3, 0)
+  B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 3, 16) B2_TC_CASE(2, 3, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 3, 0)
+  B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32)
 #undef B2_TC_CASE
   B2_FAIL("tc_scan_topk: no kernel for Kp=%d passes=%d KC=%d", Kp, passes, KC);
 }

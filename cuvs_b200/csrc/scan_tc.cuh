@@ -71,7 +71,8 @@ void tc_pack_half_norms(cudaStream_t stream, const float* hn, int64_t rows_pad, 
 /**
  * Run the scan.  For every item and every valid row r the kernel writes tc_lists_per_item() lists of KC
  * (score, position) pairs, each sorted best-first, at out_off + r * out_row_stride (+0..lists*KC-1); empty slots hold
- * (+inf, 0xffffffff).  `passes` = 3 uses hi*hi + lo*hi + hi*lo (fp32-grade products), 1 uses hi*hi.
+ * (+inf, 0xffffffff).  `passes` = 3 uses hi*hi + lo*hi + hi*lo (fp32-grade products), 2 uses (hi + lo)*hi (exact when the B rows are
+ * bf16 numbers, e.g. decoded PQ rows), 1 uses hi*hi.
  * KC must be 16 or 32 — or 0 for the dense "store" epilogue: all scores of the item are written to
  * out_score[out_off + r * out_row_stride + j], j = column offset inside the item's row range (out_pos unused).
  * With KC > 0 and out_score == null nothing is written (a bound warm-up pass: only `bound` is updated).

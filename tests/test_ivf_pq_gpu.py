@@ -155,3 +155,21 @@ def test_refine_restores_exact_order(small_index):
     assert (np.diff(rd, axis=1) >= 0).all()
     gd, gi = oracle.knn(ds, qs, 10)
     assert oracle.recall(ri, gi) >= 0.95
+
+
+def test_massive_ties_take_the_merge_fallback():
+    """Thousands of exact duplicates: every candidate of every probe ties at the pruning bound, so the per-query merge
+    cannot filter (more survivors than its buffer) and must fall back to its k-round selection; still k distinct ids,
+    all at the same distance, and a far-away row never shows up."""
+    m = _mod()
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(64).astype(np.float32)
+    ds = np.tile(base, (6000, 1))
+    ds[-1] += 50.0                                     # one outlier
+    qs = np.tile(base, (7, 1)) + 0.01
+    os.environ["CUVS_B200_PQ_PATH"] = "tc"
+    index = m.build(m.IndexParams(n_lists=4, pq_dim=32, kmeans_n_iters=5), torch.from_numpy(ds).cuda())
+    d, i = m.search(m.SearchParams(n_probes=4), index, torch.from_numpy(qs).cuda(), 10)
+    d, i = d.cpu().numpy(), i.cpu().numpy()
+    assert all(len(set(r.tolist())) == 10 for r in i) and (i >= 0).all() and (i < 5999).all()
+    assert np.allclose(d, d[:, :1], rtol=0, atol=1e-3 * max(1.0, float(np.abs(d).max())))
