@@ -183,6 +183,24 @@ class BruteForceWorkload:
         return bool(ok)
 
 
+def exact_ground_truth(dataset, queries, k, chunk=10_000_000):
+    """Exact kNN ids by our brute force, the dataset taken in chunks (bounds the temporary bf16 planes at 100M rows)."""
+    from cuvs_b200.neighbors import brute_force
+    best_d, best_i = None, None
+    for c0 in range(0, dataset.shape[0], chunk):
+        bf = brute_force.build(dataset[c0:c0 + chunk])
+        d, i = brute_force.search(bf, queries, k)
+        i = i.to(torch.int64) + c0
+        del bf
+        if best_d is None:
+            best_d, best_i = d, i
+        else:
+            dd, ii = torch.cat([best_d, d], 1), torch.cat([best_i, i], 1)
+            sel = dd.topk(k, dim=1, largest=False).indices
+            best_d, best_i = dd.gather(1, sel), ii.gather(1, sel)
+    return best_i
+
+
 class IvfPqWorkload:
     """configs[2]: ivf_pq::search 10M x 128 f32, nlist=1024 pq_dim=64 nprobe=64, batch 10k (+ exact refine to reach recall)."""
     dtype = "bf16 tensor-core scan of decoded PQ rows, fp32 accumulate; fp32 exact refine"
@@ -200,7 +218,8 @@ class IvfPqWorkload:
         self.dataset = gen_manifold(n, d, seed)
         self.queries = gen_manifold(nq, d, seed + 3087)
         t0 = time.time()
-        params = ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10)
+        params = ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10,
+                                    kmeans_trainset_fraction=min(0.5, max(4_000_000, 256 * n_lists) / n))
         if world == 1:
             self.index = ivf_pq.build(params, self.dataset)
             self.sharded = None
@@ -221,9 +240,7 @@ class IvfPqWorkload:
         self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
         self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
         # ground truth (exact, our brute force) for recall
-        bf = brute_force.build(self.dataset)
-        _, self.gt = brute_force.search(bf, self.queries, k)
-        del bf
+        self.gt = exact_ground_truth(self.dataset, self.queries, k)
         self.recall = None
 
     def _build_shard(self, params):
@@ -373,9 +390,7 @@ class CagraWorkload:
         self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
         self.h_neighbors = torch.empty((nq, k), dtype=torch.uint32).pin_memory()
         self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-        bf = brute_force.build(self.dataset)
-        _, self.gt = brute_force.search(bf, self.queries, k)
-        del bf
+        self.gt = exact_ground_truth(self.dataset, self.queries, k)
         self.recall = None
 
     def step(self, res):

@@ -591,54 +591,7 @@ void train_codebooks(resources* res, ivf_pq_index& idx, const float* resid, cons
   }
 }
 
-void ivf_pq_extend(resources* res, ivf_pq_index& idx, const float* x, int64_t n, const int64_t* new_ids, int64_t id0)
-{
-  auto s = res->stream;
-  if (n == 0) return;
-  tc_rows_tmp xp;
-  xp.build(s, x, n, idx.dim, true);
-  dbuf<uint32_t> labels(static_cast<size_t>(n), s);
-  assign_nearest(res, xp.hi.data(), xp.lo.data(), n, xp.rows_pad, xp.Kp, idx.centers_tc, labels.data(), nullptr);
-  std::vector<int64_t> add       = count_labels(s, labels.data(), n, idx.n_lists);
-  std::vector<int64_t> old_sizes = idx.lists.h_sizes.empty() ? std::vector<int64_t>(idx.n_lists, 0) : idx.lists.h_sizes;
-  std::vector<int64_t> sizes(idx.n_lists);
-  for (uint32_t l = 0; l < idx.n_lists; ++l) sizes[l] = old_sizes[l] + add[l];
-  list_layout nl;
-  nl.set_sizes(s, sizes);
-  owned<uint8_t> ncodes(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)) * idx.pq_dim);
-  owned<int64_t> nids(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)));
-  B2_CUDA(cudaMemsetAsync(ncodes.data(), 0, static_cast<size_t>(nl.rows_total) * idx.pq_dim, s));
-  count_launch();
-  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, -1);
-  if (idx.lists.rows_total > 0) {
-    dbuf<int64_t> dst_old(static_cast<size_t>(idx.lists.rows_total), s);
-    count_launch(2);
-    remap_rows_kernel<<<idx.n_lists, 128, 0, s>>>(idx.lists.d_offsets.data(), nl.d_offsets.data(), idx.lists.d_sizes.data(), idx.n_lists,
-                                                   dst_old.data());
-    move_codes_kernel<<<blocks_for(idx.lists.rows_total * idx.pq_dim, 256), 256, 0, s>>>(
-      idx.codes.data(), idx.ids.data(), idx.lists.rows_total, idx.pq_dim, dst_old.data(), ncodes.data(), nids.data());
-    B2_CUDA(cudaGetLastError());
-  }
-  dbuf<int64_t> dst_new(static_cast<size_t>(n), s);
-  place_rows(s, labels.data(), n, nl, old_sizes, dst_new.data());
-  // encode: rotate, residual, nearest code per subspace
-  dbuf<float> xr(static_cast<size_t>(n) * idx.rot_dim, s), rs(static_cast<size_t>(n) * idx.rot_dim, s);
-  rotate_rows(s, x, n, idx.dim, idx.rotation.data(), idx.rot_dim, xr.data());
-  count_launch(3);
-  residual_kernel<<<blocks_for(n * idx.rot_dim, 256), 256, 0, s>>>(xr.data(), labels.data(), idx.centers_rot.data(), n, idx.rot_dim, rs.data());
-  const size_t smem = static_cast<size_t>(idx.pq_len) * idx.book() * sizeof(float);
-  pq_assign_kernel<<<dim3(blocks_for(n, 128), idx.pq_dim), 128, smem, s>>>(
-    rs.data(), n, idx.rot_dim, idx.pq_dim, idx.pq_len, idx.book(), idx.pq_centers.data(),
-    idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_CLUSTER, labels.data(), ncodes.data(), dst_new.data());
-  set_ids_kernel<<<blocks_for(n, 256), 256, 0, s>>>(dst_new.data(), new_ids, id0, n, nids.data());
-  B2_CUDA(cudaGetLastError());
-  B2_CUDA(cudaStreamSynchronize(s));
-  idx.codes = std::move(ncodes);
-  idx.ids   = std::move(nids);
-  idx.lists = std::move(nl);
-  refresh_decoded(res, idx);
-}
-
+// rows of `t` in device-resident chunks of at most 512 MiB (host tensors are staged through one reusable buffer)
 template <typename Fn>
 void for_device_chunks(resources* res, const DLTensor& t, int d, Fn&& fn)
 {
@@ -656,6 +609,69 @@ void for_device_chunks(resources* res, const DLTensor& t, int d, Fn&& fn)
       fn(buf.data(), rows, r0);
     }
   }
+}
+
+// Insert the rows of `t` (ids new_ids[i] or id0 + i).  Two passes over the chunks so that the lists are laid out ONCE for
+// the whole insertion: (1) label every row and count per list, (2) encode every chunk straight into its final place.  The
+// decoded rows are refreshed once at the end.  (Inserting chunk by chunk would re-pack and re-decode the whole index per
+// chunk: quadratic in the index size, minutes at 100M rows.)
+void ivf_pq_extend(resources* res, ivf_pq_index& idx, const DLTensor& t, const int64_t* new_ids, int64_t id0)
+{
+  auto s          = res->stream;
+  const int64_t n = t.shape[0];
+  if (n == 0) return;
+  dbuf<uint32_t> labels(static_cast<size_t>(n), s);
+  std::vector<int64_t> old_sizes = idx.lists.h_sizes.empty() ? std::vector<int64_t>(idx.n_lists, 0) : idx.lists.h_sizes;
+  std::vector<int64_t> sizes     = old_sizes;
+  std::vector<std::vector<int64_t>> chunk_add;
+  for_device_chunks(res, t, idx.dim, [&](const float* x, int64_t rows, int64_t r0) {
+    tc_rows_tmp xp;
+    xp.build(s, x, rows, idx.dim, true);
+    assign_nearest(res, xp.hi.data(), xp.lo.data(), rows, xp.rows_pad, xp.Kp, idx.centers_tc, labels.data() + r0, nullptr);
+    chunk_add.push_back(count_labels(s, labels.data() + r0, rows, idx.n_lists));
+    for (uint32_t l = 0; l < idx.n_lists; ++l) sizes[l] += chunk_add.back()[l];
+  });
+  list_layout nl;
+  nl.set_sizes(s, sizes);
+  owned<uint8_t> ncodes(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)) * idx.pq_dim);
+  owned<int64_t> nids(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)));
+  B2_CUDA(cudaMemsetAsync(ncodes.data(), 0, static_cast<size_t>(nl.rows_total) * idx.pq_dim, s));
+  count_launch();
+  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, -1);
+  if (idx.lists.rows_total > 0) {
+    dbuf<int64_t> dst_old(static_cast<size_t>(idx.lists.rows_total), s);
+    count_launch(2);
+    remap_rows_kernel<<<idx.n_lists, 128, 0, s>>>(idx.lists.d_offsets.data(), nl.d_offsets.data(), idx.lists.d_sizes.data(), idx.n_lists,
+                                                   dst_old.data());
+    move_codes_kernel<<<blocks_for(idx.lists.rows_total * idx.pq_dim, 256), 256, 0, s>>>(
+      idx.codes.data(), idx.ids.data(), idx.lists.rows_total, idx.pq_dim, dst_old.data(), ncodes.data(), nids.data());
+    B2_CUDA(cudaGetLastError());
+  }
+  std::vector<int64_t> fill = old_sizes;  // rows already placed in each list
+  size_t ci = 0;
+  for_device_chunks(res, t, idx.dim, [&](const float* x, int64_t rows, int64_t r0) {
+    dbuf<int64_t> dst_new(static_cast<size_t>(rows), s);
+    place_rows(s, labels.data() + r0, rows, nl, fill, dst_new.data());
+    for (uint32_t l = 0; l < idx.n_lists; ++l) fill[l] += chunk_add[ci][l];
+    ++ci;
+    // encode: rotate, residual, nearest code per subspace
+    dbuf<float> xr(static_cast<size_t>(rows) * idx.rot_dim, s), rs(static_cast<size_t>(rows) * idx.rot_dim, s);
+    rotate_rows(s, x, rows, idx.dim, idx.rotation.data(), idx.rot_dim, xr.data());
+    count_launch(3);
+    residual_kernel<<<blocks_for(rows * idx.rot_dim, 256), 256, 0, s>>>(xr.data(), labels.data() + r0, idx.centers_rot.data(), rows,
+                                                                         idx.rot_dim, rs.data());
+    const size_t smem = static_cast<size_t>(idx.pq_len) * idx.book() * sizeof(float);
+    pq_assign_kernel<<<dim3(blocks_for(rows, 128), idx.pq_dim), 128, smem, s>>>(
+      rs.data(), rows, idx.rot_dim, idx.pq_dim, idx.pq_len, idx.book(), idx.pq_centers.data(),
+      idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_CLUSTER, labels.data() + r0, ncodes.data(), dst_new.data());
+    set_ids_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(dst_new.data(), new_ids ? new_ids + r0 : nullptr, id0 + r0, rows, nids.data());
+    B2_CUDA(cudaGetLastError());
+  });
+  B2_CUDA(cudaStreamSynchronize(s));
+  idx.codes = std::move(ncodes);
+  idx.ids   = std::move(nids);
+  idx.lists = std::move(nl);
+  refresh_decoded(res, idx);
 }
 
 void init_shape(ivf_pq_index& idx, const cuvsIvfPqIndexParams& p, int dim)
@@ -733,7 +749,7 @@ ivf_pq_index* ivf_pq_build(resources* res, const cuvsIvfPqIndexParams& p, const 
   idx->ids.alloc(1);
   refresh_decoded(res, *idx);
   if (p.add_data_on_build) {
-    for_device_chunks(res, ds, d, [&](const float* x, int64_t rows, int64_t r0) { ivf_pq_extend(res, *idx, x, rows, nullptr, r0); });
+    ivf_pq_extend(res, *idx, ds, nullptr, 0);
   }
   return idx.release();
 }
@@ -1142,9 +1158,7 @@ cuvsError_t cuvsIvfPqExtend(cuvsResources_t res, DLManagedTensor* new_vectors, D
       }
     }
     const int64_t id0 = idx.lists.size;
-    for_device_chunks(r, v, idx.dim, [&](const float* x, int64_t rows, int64_t r0) {
-      ivf_pq_extend(r, idx, x, rows, ids ? ids + r0 : nullptr, id0 + r0);
-    });
+    ivf_pq_extend(r, idx, v, ids, id0);
   });
 }
 
