@@ -51,9 +51,15 @@ struct cfg {
   static constexpr int NA = PASSES >= 2 ? 2 : 1;  // A planes resident in shared memory
   static constexpr int NB = PASSES == 3 ? 2 : 1;  // B planes streamed
   static constexpr int threads     = 64 + kEpiThreads;
-  static constexpr int stages      = NB == 2 ? 3 : (NA == 2 ? 5 : 6);
-  static constexpr int a_bytes     = NA * KB * kTileBytes;
-  static constexpr int stage_bytes = NB * kTileBytes + kExtBytes;  // ext slot used by the kb == 0 stage of a tile
+  // KB = 1, 2: the query tile (KB k-blocks of 64) stays resident in shared memory for a whole work item.
+  // KB = 0: "streamed" — any padded K (multiple of 64): the A k-block travels through the ring next to the B k-block
+  //         (dims > 128; costs one extra 16 KB L2 read per plane and k-block, the tile's MMA work grows with K as well).
+  static constexpr bool streamed   = KB == 0;
+  static constexpr int stages      = streamed ? (PASSES == 1 ? 4 : (PASSES == 2 ? 3 : 2)) : (NB == 2 ? 3 : (NA == 2 ? 5 : 6));
+  static constexpr int a_bytes     = streamed ? 0 : NA * KB * kTileBytes;
+  static constexpr int b_off       = streamed ? NA * kTileBytes : 0;             // B planes inside a stage
+  static constexpr int x_off       = b_off + NB * kTileBytes;                    // half-norm block (kb == 0 stage of a tile)
+  static constexpr int stage_bytes = x_off + kExtBytes;
   static constexpr int n_bars      = 2 * stages + 2 + 2 * kAccBufs + 2 * kSched;
   static constexpr size_t smem     = 1024 /*align slack*/ + a_bytes + kExtBytes /*ones*/ + stages * stage_bytes +
                                  kQueue * kEpiThreads * 8 /*queues*/ + n_bars * 8 + kSched * 4 + 16;
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(64 + kEpiThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_x, const tc_item* __restrict__ items, int n_items_host,
-               const int* __restrict__ n_items_dev, int* __restrict__ sched_counter, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
+               const int* __restrict__ n_items_dev, int kblocks_rt, int* __restrict__ sched_counter, float* __restrict__ out_score, uint32_t* __restrict__ out_pos,
                int64_t out_row_stride, int dbg_flags, tc_bound bound)
 {
   const int dbg_skip_epilogue = dbg_flags & 1;
@@ -75,6 +81,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t nst          = (dbg_flags >> 8) ? min(static_cast<uint32_t>(dbg_flags >> 8), static_cast<uint32_t>(cfg<KB, PASSES>::stages)) : cfg<KB, PASSES>::stages;  // ring depth (experiment knob)
   using C = cfg<KB, PASSES>;
   constexpr int NA = C::NA, NB = C::NB;
+  const int nkb = C::streamed ? kblocks_rt : KB;  // k-blocks of 64 per tile
   const int n_items = n_items_dev ? *n_items_dev : n_items_host;
   // 1024-byte alignment is what SWIZZLE_128B operand tiles need; declared on the array (no integer
   // round-trip of the pointer) so that the compiler keeps every access in the shared address space.
@@ -164,37 +171,43 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       item.a_row0  = __shfl_sync(0xffffffffu, item.a_row0, 0);
       item.b_row0  = __shfl_sync(0xffffffffu, item.b_row0, 0);
       item.n_tiles = __shfl_sync(0xffffffffu, item.n_tiles, 0);
-      ptx::mbar_wait(a_empty, a_phase ^ 1);
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
+      if constexpr (!C::streamed) {
+        ptx::mbar_wait(a_empty, a_phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(a_full, C::a_bytes);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::tma_load_2d(sA + (0 * KB + kb) * kTileBytes, &tmA_hi, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
-          if (NA == 2)
-            ptx::tma_load_2d(sA + (1 * KB + kb) * kTileBytes, &tmA_lo, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::tma_load_2d(sA + (0 * KB + kb) * kTileBytes, &tmA_hi, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
+            if (NA == 2)
+              ptx::tma_load_2d(sA + (1 * KB + kb) * kTileBytes, &tmA_lo, a_full, kb * 64, static_cast<int32_t>(item.a_row0));
+          }
         }
+        a_phase ^= 1;
       }
-      a_phase ^= 1;
       for (uint32_t t = 0; t < item.n_tiles; ++t) {
         const int32_t brow = static_cast<int32_t>(item.b_row0 + t * 128);
         if (prefetch_on && lane == 0 && t + kPrefetch < item.n_tiles) {
           const int32_t prow = brow + kPrefetch * 128;
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             ptx::tma_prefetch_2d(&tmB_hi, kb * 64, prow);
             if (NB == 2) ptx::tma_prefetch_2d(&tmB_lo, kb * 64, prow);
           }
           ptx::tma_prefetch_2d(&tmB_x, 0, prow);
         }
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&full[stage], NB * kTileBytes + (kb == 0 ? kExtBytes : 0));
+            ptx::mbar_arrive_expect_tx(&full[stage], C::x_off + (kb == 0 ? kExtBytes : 0));
             uint8_t* dst = sB + stage * C::stage_bytes;
-            ptx::tma_load_2d(dst, &tmB_hi, &full[stage], kb * 64, brow);
-            if (NB == 2) ptx::tma_load_2d(dst + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
-            if (kb == 0) ptx::tma_load_2d(dst + NB * kTileBytes, &tmB_x, &full[stage], 0, brow);
+            if constexpr (C::streamed) {
+              ptx::tma_load_2d(dst, &tmA_hi, &full[stage], kb * 64, static_cast<int32_t>(item.a_row0));
+              if (NA == 2) ptx::tma_load_2d(dst + kTileBytes, &tmA_lo, &full[stage], kb * 64, static_cast<int32_t>(item.a_row0));
+            }
+            ptx::tma_load_2d(dst + C::b_off, &tmB_hi, &full[stage], kb * 64, brow);
+            if (NB == 2) ptx::tma_load_2d(dst + C::b_off + kTileBytes, &tmB_lo, &full[stage], kb * 64, brow);
+            if (kb == 0) ptx::tma_load_2d(dst + C::x_off, &tmB_x, &full[stage], 0, brow);
           }
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
@@ -215,8 +228,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
       const uint32_t n_tiles = __shfl_sync(0xffffffffu, items[it].n_tiles, 0);
-      ptx::mbar_wait(a_full, a_phase);
-      ptx::tc_fence_after_sync();
+      if constexpr (!C::streamed) {
+        ptx::mbar_wait(a_full, a_phase);
+        ptx::tc_fence_after_sync();
+      }
       for (uint32_t t = 0; t < n_tiles; ++t) {
         if (dbg_flags & 32) ptx::mbar_wait_poll(&tempty[acc], acc_phase ^ 1);
         else if (dbg_flags & 64) ptx::mbar_wait_hint(&tempty[acc], acc_phase ^ 1, 1000);
@@ -224,18 +239,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * 128;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              // +2 per K = 16 step (32 bytes >> 4); k-block kb / plane p of A sit (p * KB + kb) * 1024 further (16 KB >> 4)
-              const uint32_t ah = a_lo0 + (0 * KB + kb) * 1024 + k * 2;
-              const uint32_t bh = b_lo + k * 2;
+              // +2 per K = 16 step (32 bytes >> 4).  Resident A: k-block kb / plane p sit (p * KB + kb) * 1024 further
+              // (16 KB >> 4).  Streamed A: the planes lead the stage, the B planes follow at b_off.
+              const uint32_t ah = (C::streamed ? b_lo : a_lo0 + (0 * KB + kb) * 1024) + k * 2;
+              const uint32_t bh = b_lo + (C::b_off >> 4) + k * 2;
               ptx::mma_bf16_ss_lohi(d_tmem, ah, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
               if (NA == 2) {
-                const uint32_t al = a_lo0 + (1 * KB + kb) * 1024 + k * 2;
+                const uint32_t al = (C::streamed ? b_lo + 1024 : a_lo0 + (1 * KB + kb) * 1024) + k * 2;
                 ptx::mma_bf16_ss_lohi(d_tmem, al, ptx::kDescHiSw128, bh, ptx::kDescHiSw128, idesc, 1u);
               }
               if (NB == 2) {
@@ -244,7 +260,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               }
             }
             if (kb == 0)  // -= |x|^2/2
-              ptx::mma_bf16_ss_lohi(d_tmem, ones_lo, ptx::kDescHiSw32, b_lo + NB * 1024, ptx::kDescHiSw32, idesc, 1u);
+              ptx::mma_bf16_ss_lohi(d_tmem, ones_lo, ptx::kDescHiSw32, b_lo + (C::x_off >> 4), ptx::kDescHiSw32, idesc, 1u);
             ptx::mma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
           }
           b_lo += C::stage_bytes >> 4;
@@ -253,8 +269,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (ptx::elect_one()) ptx::mma_commit(&tfull[acc]);  // accumulator complete -> epilogue
         if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
-      if (ptx::elect_one()) ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
-      a_phase ^= 1;
+      if constexpr (!C::streamed) {
+        if (ptx::elect_one()) ptx::mma_commit(a_empty);  // all MMAs reading this A tile are done
+        a_phase ^= 1;
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps, 1 row x 64 columns per thread)
@@ -484,7 +502,7 @@ int env_int(const char* name, int dflt)
 template <int KB, int PASSES, int KC>
 void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
             const CUtensorMap& b_lo, const CUtensorMap& b_x, const tc_item* items, int n_items, const int* n_items_dev,
-            float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound, bool dynamic)
+            float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound& bound, bool dynamic, int kblocks)
 {
   auto kern = tc_scan_kernel<KB, PASSES, KC>;
   using C   = cfg<KB, PASSES>;
@@ -506,7 +524,7 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
   }
   timed_section ts("tc_scan", stream);
   count_launch();
-  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, sched.data(), out_score,
+  kern<<<grid, C::threads, C::smem, stream>>>(a_hi, a_lo, b_hi, b_lo, b_x, items, n_items, n_items_dev, kblocks, sched.data(), out_score,
                                                out_pos, out_row_stride, skip_epi, bound);
   B2_CUDA(cudaGetLastError());
 }
@@ -583,7 +601,7 @@ bool tc_supported(int device, int d)
 {
   int major = 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return false;
-  return major == 10 && d >= 1 && tc_pad_k(d) <= 128;
+  return major == 10 && d >= 1 && tc_pad_k(d) <= kTcMaxK;
 }
 
 void tc_split_planes(cudaStream_t stream, const float* x, int64_t n, int64_t ld, int d, int Kp, __nv_bfloat16* hi,
@@ -619,7 +637,7 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
                   float* out_score, uint32_t* out_pos, int64_t out_row_stride, const tc_bound* bound, bool dynamic_schedule)
 {
   if (n_items == 0) return;  // n_items is the host-side upper bound (grid sizing); *n_items_dev, when given, is the exact count
-  B2_EXPECTS(Kp == 64 || Kp == 128, "tc_scan_topk: padded K must be 64 or 128 (got %d)", Kp);
+  B2_EXPECTS(Kp >= 64 && Kp % 64 == 0 && Kp <= kTcMaxK, "tc_scan_topk: padded K must be a multiple of 64 up to %d (got %d)", kTcMaxK, Kp);
   B2_EXPECTS(KC == 0 || KC == 16 || KC == 32, "tc_scan_topk: KC must be 0 (store), 16 or 32");
   B2_EXPECTS(passes >= 1 && passes <= 3, "tc_scan_topk: passes must be 1, 2 or 3");
   B2_EXPECTS(passes == 1 || a_lo, "tc_scan_topk: the A lo plane is required for 2- and 3-pass mode");
@@ -633,12 +651,15 @@ void tc_scan_topk(cudaStream_t stream, int device, const __nv_bfloat16* a_hi, co
   CUtensorMap mAl = passes >= 2 ? make_plane_map(a_lo, a_rows_pad, Kp) : mA;
   CUtensorMap mBl = passes == 3 ? make_plane_map(b_lo, b_rows_pad, Kp) : mB;
   CUtensorMap mBx = make_ext_map(hx, b_rows_pad);
+  const int kb_case = Kp <= 128 ? Kp / 64 : 0;  // 0 = streamed A (any K)
 #define B2_TC_CASE(KB_, P_, KC_)                                                                                       \
-  if (Kp == 64 * KB_ && passes == P_ && KC == KC_)                                                                     \
-    return launch<KB_, P_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd, dynamic_schedule);
+  if (kb_case == KB_ && passes == P_ && KC == KC_)                                                                     \
+    return launch<KB_, P_, KC_>(stream, sms, mA, mAl, mB, mBl, mBx, items_dev, n_items, n_items_dev, out_score, out_pos, out_row_stride, bnd, dynamic_schedule, Kp / 64);
   B2_TC_CASE(1, 1, 16) B2_TC_CASE(1, 1, 32) B2_TC_CASE(1, 3, 16) B2_TC_CASE(1, 3, 32) B2_TC_CASE(1, 1, 0) B2_TC_CASE(1, 3, 0)
   B2_TC_CASE(2, 1, 16) B2_TC_CASE(2, 1, 32) B2_TC_CASE(2, 3, 16) B2_TC_CASE(2, 3, 32) B2_TC_CASE(2, 1, 0) B2_TC_CASE(2, 3, 0)
   B2_TC_CASE(1, 2, 16) B2_TC_CASE(1, 2, 32) B2_TC_CASE(2, 2, 16) B2_TC_CASE(2, 2, 32)
+  B2_TC_CASE(0, 1, 16) B2_TC_CASE(0, 1, 32) B2_TC_CASE(0, 1, 0) B2_TC_CASE(0, 2, 16) B2_TC_CASE(0, 2, 32)
+  B2_TC_CASE(0, 3, 16) B2_TC_CASE(0, 3, 32) B2_TC_CASE(0, 3, 0)
 #undef B2_TC_CASE
   B2_FAIL("tc_scan_topk: no kernel for Kp=%d passes=%d KC=%d", Kp, passes, KC);
 }

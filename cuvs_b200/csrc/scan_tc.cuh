@@ -13,6 +13,7 @@
 namespace b200 {
 
 constexpr int kTcTile = 128;  // rows of A (queries) and rows of B (dataset) per MMA tile
+constexpr int kTcMaxK = 2048; // largest padded dimension (K <= 128: query tile resident in smem; above: streamed k-blocks)
 
 /** One unit of work: 128 query rows against a contiguous range of 128-row dataset tiles. */
 struct tc_item {
@@ -49,7 +50,7 @@ inline int64_t tc_pad_rows(int64_t n) { return (n + kTcTile - 1) / kTcTile * kTc
  *  64 of the tile's 128 columns).  Every list holds KC entries; list j sits at +j*KC. */
 int tc_lists_per_item();
 
-/** True when the device/shape combination is served by the tcgen05 kernel (sm_100, Kp <= 128). */
+/** True when the device/shape combination is served by the tcgen05 kernel (sm_100, padded dim <= kTcMaxK). */
 bool tc_supported(int device, int d);
 
 /**

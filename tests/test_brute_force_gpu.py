@@ -64,7 +64,8 @@ def test_reference_label_case():
 
 
 @pytest.mark.parametrize("n,d,nq,k", [(20000, 128, 300, 10), (5000, 96, 130, 5), (3001, 33, 77, 1),
-                                       (9000, 64, 128, 24), (1000, 128, 5, 10), (70000, 128, 257, 10)])
+                                       (9000, 64, 128, 24), (1000, 128, 5, 10), (70000, 128, 257, 10),
+                                       (6000, 200, 140, 10), (4000, 768, 64, 10)])  # dims > 128: streamed k-blocks
 @pytest.mark.parametrize("metric", ["sqeuclidean"])
 def test_exact_match_uniform(n, d, nq, k, metric):
     ds, qs = uniform(n, d, 1234), uniform(nq, d, 4321)

@@ -33,7 +33,8 @@ def _oracle_search(index, ds, qs, n_probes, k, metric):
 
 @pytest.mark.parametrize("n,d,n_lists,n_probes,k,metric", [
     (20000, 128, 64, 8, 10, "sqeuclidean"), (20000, 96, 100, 100, 10, "sqeuclidean"), (8000, 64, 32, 6, 16, "euclidean"),
-    (10000, 33, 50, 10, 5, "inner_product"), (30000, 128, 128, 16, 32, "sqeuclidean"), (6000, 16, 20, 5, 1, "sqeuclidean")])
+    (10000, 33, 50, 10, 5, "inner_product"), (30000, 128, 128, 16, 32, "sqeuclidean"), (6000, 16, 20, 5, 1, "sqeuclidean"),
+    (12000, 256, 40, 8, 10, "sqeuclidean")])
 def test_search_matches_oracle(n, d, n_lists, n_probes, k, metric):
     m = _mod()
     ds, centers = clustered(n, d, 5, n_centers=max(8, n_lists // 2))

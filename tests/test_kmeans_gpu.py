@@ -15,7 +15,7 @@ def _km():
     return kmeans
 
 
-@pytest.mark.parametrize("n,d,k", [(10000, 64, 17), (5000, 128, 300), (3000, 5, 2), (70000, 96, 1024)])
+@pytest.mark.parametrize("n,d,k", [(10000, 64, 17), (5000, 128, 300), (3000, 5, 2), (70000, 96, 1024), (8000, 300, 50)])
 def test_predict_matches_oracle_assignment(n, d, k):
     km = _km()
     x = uniform(n, d, 3)
