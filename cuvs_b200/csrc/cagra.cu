@@ -146,6 +146,8 @@ struct cagra_launch {
   int64_t* out_idx64;
   float* out_dist;
   uint32_t* out_iters;
+  const uint32_t* keep_bits;  // bitset pre-filter over node ids (bit = 1 keeps), null = none
+  int64_t n_bits;
 };
 
 // squared L2 / negative dot between the smem query and a dataset row, computed by a team of 8 lanes
@@ -173,6 +175,11 @@ __device__ __forceinline__ float team_distance(const float* __restrict__ row, co
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   return acc;
+}
+
+__device__ __forceinline__ bool node_kept(const cagra_launch& p, uint32_t id)
+{
+  return static_cast<int64_t>(id) < p.n_bits && ((p.keep_bits[id >> 5] >> (id & 31)) & 1u);
 }
 
 // EI = itopk / 32, EC = (search_width * degree rounded up to 32) / 32 ; buffer = EI + EC keys per lane
@@ -265,7 +272,9 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const uint32_t pid = __shfl_sync(0xffffffffu, id, src);
-        if (lane == src) key[e] |= kMsb;  // mark as used
+        // mark as used; a node the filter rejects may serve as a stepping stone ONCE and then leaves the list
+        // (search_single_cta_jit.cuh:297-316: filtered parents are invalidated after their children were expanded)
+        if (lane == src) key[e] = (p.keep_bits != nullptr && !node_kept(p, pid)) ? ~0ull : (key[e] | kMsb);
         if (lane == 0) sparent[n_parents] = pid;
         ++n_parents;
       }
@@ -318,6 +327,15 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
     ++iter;
   }
 
+  // ---- pre-filter post-processing (search_single_cta_jit.cuh:321-334): drop rejected nodes, valid ones move up
+  if (p.keep_bits != nullptr) {
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      if (e >= EI) key[e] = ~0ull;
+      else if (key[e] != ~0ull && !node_kept(p, static_cast<uint32_t>(key[e]) & ~kMsb)) key[e] = ~0ull;
+    }
+    warp_bitonic_sort<EB>(key, lane);
+  }
   // ---- results: first k entries of the sorted list
 #pragma unroll
   for (int e = 0; e < EI; ++e) {
@@ -399,7 +417,7 @@ void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
 }
 
 void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchParams& sp, const float* queries, int64_t nq, int k,
-                  uint32_t* out32, int64_t* out64, float* out_dist)
+                  uint32_t* out32, int64_t* out64, float* out_dist, const uint32_t* keep_bits = nullptr, int64_t n_bits = 0)
 {
   auto s = res->stream;
   if (nq == 0) return;
@@ -419,6 +437,7 @@ void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchP
   p.num_random_samplings = static_cast<int>(std::max<uint32_t>(sp.num_random_samplings, 1));
   p.rand_xor_mask = sp.rand_xor_mask;
   p.out_idx32 = out32; p.out_idx64 = out64; p.out_dist = out_dist; p.out_iters = nullptr;
+  p.keep_bits = keep_bits; p.n_bits = n_bits;
   dbuf<uint32_t> gh;
   if (pl.small_hash_bitlen == 0) {
     gh.alloc(static_cast<size_t>(nq) << pl.hash_bitlen, s);
@@ -863,10 +882,19 @@ cuvsError_t cuvsCagraSearch(cuvsResources_t res, cuvsCagraSearchParams_t params,
     B2_EXPECTS(dl_is_c_contiguous(queries) && dl_is_c_contiguous(neighbors) && dl_is_c_contiguous(distances), "tensors must be row-major contiguous");
     B2_EXPECTS(queries.shape[1] == idx.dim, "queries dim (%lld) != index dim (%d)", (long long)queries.shape[1], idx.dim);
     B2_EXPECTS(neighbors.shape[0] == queries.shape[0] && distances.shape[0] == queries.shape[0] && distances.shape[1] == neighbors.shape[1], "neighbors/distances shape mismatch");
-    B2_EXPECTS(filter.type == NO_FILTER, "cagra search: pre-filters are not supported by this build yet");
+    const uint32_t* keep = nullptr;
+    int64_t n_bits       = 0;
+    if (filter.type != NO_FILTER) {
+      B2_EXPECTS(filter.type == BITSET, "cagra search: only bitset pre-filters are supported (c/src/neighbors/cagra.cpp)");
+      auto ft = reinterpret_cast<DLManagedTensor*>(filter.addr);
+      B2_EXPECTS(ft != nullptr && dl_is_device(ft->dl_tensor), "prefilter should have device compatible memory");
+      keep   = dl_ptr<uint32_t>(ft->dl_tensor);
+      n_bits = ft->dl_tensor.shape[0] * 32;
+    }
     const bool u32 = dl_is(neighbors, kDLUInt, 32);
     cagra_search(r, idx, *params, dl_ptr<float>(queries), queries.shape[0], static_cast<int>(neighbors.shape[1]),
-                 u32 ? dl_ptr<uint32_t>(neighbors) : nullptr, u32 ? nullptr : dl_ptr<int64_t>(neighbors), dl_ptr<float>(distances));
+                 u32 ? dl_ptr<uint32_t>(neighbors) : nullptr, u32 ? nullptr : dl_ptr<int64_t>(neighbors), dl_ptr<float>(distances),
+                 keep, n_bits);
   });
 }
 

@@ -86,6 +86,18 @@ __global__ void half_norms_masked_kernel(const float* __restrict__ xn, const int
   hn[i] = ids[i] < 0 ? INFINITY : (zero ? 0.f : 0.5f * xn[i]);
 }
 
+// same, additionally hiding every row whose source id is not kept by the bitset (bit = 1 keeps): the filtered search
+// scans against this temporary plane, so excluded rows score -inf inside the tensor-core kernel and can never be candidates
+__global__ void half_norms_filtered_kernel(const float* __restrict__ xn, const int64_t* __restrict__ ids, int64_t n, bool zero,
+                                           const uint32_t* __restrict__ bits, int64_t n_bits, float* __restrict__ hn)
+{
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  const bool keep  = id >= 0 && id < n_bits && ((bits[id >> 5] >> (id & 31)) & 1u);
+  hn[i]            = keep ? (zero ? 0.f : 0.5f * xn[i]) : INFINITY;
+}
+
 __global__ void rsqrt_rows_kernel(const float* __restrict__ xn, float* __restrict__ out, int64_t n)
 {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -271,7 +283,7 @@ ivf_flat_index* ivf_flat_build(resources* res, const cuvsIvfFlatIndexParams& p, 
 }
 
 void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probes, const DLTensor& qt, const DLTensor& nt,
-                     const DLTensor& dt)
+                     const DLTensor& dt, const uint32_t* keep_bits = nullptr, int64_t n_bits = 0)
 {
   auto s           = res->stream;
   const int64_t nq = qt.shape[0];
@@ -301,6 +313,21 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   dbuf<uint32_t> probes(static_cast<size_t>(nq) * n_probes, s);
   coarse_select(res, qp, idx.centers_tc, static_cast<int>(n_probes), probes.data(), nullptr);
 
+  // ---- 1b. bitset pre-filter (cuvs::neighbors::filtering::bitset_filter): one pass over the half-norm plane
+  dbuf<__nv_bfloat16> hx_f;
+  const __nv_bfloat16* hx = idx.hx.data();
+  if (keep_bits != nullptr && idx.lists.rows_total > 0) {
+    const int64_t R = idx.lists.rows_total;
+    dbuf<float> hn(static_cast<size_t>(R), s);
+    hx_f.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * 16, s);
+    count_launch();
+    half_norms_filtered_kernel<<<blocks_for(R, 256), 256, 0, s>>>(idx.xn.data(), idx.ids.data(), R, !is_l2(idx.metric), keep_bits, n_bits,
+                                                                   hn.data());
+    B2_CUDA(cudaGetLastError());
+    tc_pack_half_norms(s, hn.data(), R, hx_f.data());
+    hx = hx_f.data();
+  }
+
   // ---- 2. bucket (query, probe) pairs by list
   const int KC    = k <= 16 ? 16 : 32;
   const int lists = tc_lists_per_item();
@@ -324,7 +351,7 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
     bnd.idx  = pb.pair_query.data();
     timed_section ts("ivf_flat_scan", s);
     tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.hi.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                 idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
+                 idx.Kp, hx, pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
   }
 
   // ---- 4. per query: merge probes by approximate score, exact re-score, ids
@@ -470,8 +497,16 @@ cuvsError_t cuvsIvfFlatSearch(cuvsResources_t res, cuvsIvfFlatSearchParams_t par
     B2_EXPECTS(queries.dtype.code == index->dtype.code && queries.dtype.bits == index->dtype.bits, "type mismatch between index and queries");
     B2_EXPECTS(queries.ndim == 2 && neighbors.ndim == 2 && distances.ndim == 2, "queries/neighbors/distances must be 2-D");
     B2_EXPECTS(dl_is_c_contiguous(queries) && dl_is_c_contiguous(neighbors) && dl_is_c_contiguous(distances), "tensors must be row-major contiguous");
-    B2_EXPECTS(filter.type == NO_FILTER, "ivf_flat search: pre-filters are not supported by this build yet");
-    ivf_flat_search(r, idx, params->n_probes, queries, neighbors, distances);
+    const uint32_t* keep = nullptr;
+    int64_t n_bits       = 0;
+    if (filter.type != NO_FILTER) {
+      B2_EXPECTS(filter.type == BITSET, "ivf_flat search: only bitset pre-filters are supported (as in the reference)");
+      auto ft = reinterpret_cast<DLManagedTensor*>(filter.addr);
+      B2_EXPECTS(ft != nullptr && dl_is_device(ft->dl_tensor), "prefilter should have device compatible memory");
+      keep   = dl_ptr<uint32_t>(ft->dl_tensor);
+      n_bits = ft->dl_tensor.shape[0] * 32;
+    }
+    ivf_flat_search(r, idx, params->n_probes, queries, neighbors, distances, keep, n_bits);
   });
 }
 

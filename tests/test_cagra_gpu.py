@@ -99,3 +99,39 @@ def test_build_search_save_load(tmp_path):
     again = m.load(str(tmp_path / "cagra.idx"))
     d2, i2 = m.search(m.SearchParams(itopk_size=64), again, torch.from_numpy(qs).cuda(), 10)
     assert torch.equal(i1.to(torch.int64), i2.to(torch.int64)) and torch.equal(d1, d2)
+
+
+def _bitset(keep):
+    keep = np.asarray(keep, bool)
+    bits = np.packbits(np.concatenate([keep, np.zeros((-len(keep)) % 32, bool)]), bitorder="little").view(np.int32)
+    from cuvs_b200.neighbors import filters
+    return filters.from_bitset(torch.from_numpy(bits.copy()).cuda())
+
+
+def test_reference_known_answers_bitset_filtered():
+    """c/tests/neighbors/ann_cagra_c.cu filtered case: same 4x2 data, half of the rows removed by a bitset pre-filter."""
+    m = _mod()
+    case = [c for c in GOLD["cases"] if c["name"] == "cagra_c_4x2_k1_bitset_filtered"][0]
+    ds = np.array(case["dataset"], np.float32)
+    qs = np.array(case["queries"], np.float32)
+    index = m.build(m.IndexParams(graph_degree=2, intermediate_graph_degree=3), torch.from_numpy(ds).cuda())
+    d, i = m.search(m.SearchParams(itopk_size=32), index, torch.from_numpy(qs).cuda(), 1, filter=_bitset(np.isin(np.arange(len(ds)), case["filter_keep"])))
+    assert i.cpu().numpy().astype(np.int64).tolist() == case["neighbors"]
+    np.testing.assert_allclose(d.cpu().numpy(), np.array(case["distances"], np.float32), atol=case["eps"])
+
+
+def test_bitset_prefilter_on_a_real_graph():
+    """Filtered nodes are walked through but never returned; recall against exact kNN over the kept rows."""
+    m = _mod()
+    rng = np.random.default_rng(5)
+    A = (rng.standard_normal((8, 64)) / np.sqrt(8)).astype(np.float32)
+    ds = (rng.standard_normal((20000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((20000, 64)).astype(np.float32))
+    qs = (rng.standard_normal((200, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((200, 64)).astype(np.float32))
+    index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
+    keep = rng.random(20000) < 0.5
+    d, i = m.search(m.SearchParams(itopk_size=128), index, torch.from_numpy(qs).cuda(), 10, filter=_bitset(keep))
+    i = i.cpu().numpy().astype(np.int64)
+    assert keep[i].all(), "a filtered-out node was returned"
+    kept = np.flatnonzero(keep)
+    gd, gi = oracle.knn(ds[kept], qs, 10)
+    assert oracle.recall(i, kept[gi]) >= 0.9

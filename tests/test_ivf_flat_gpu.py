@@ -99,3 +99,26 @@ def test_out_of_bounds_record_when_probed_lists_are_small():
     i = i.cpu().numpy()
     assert (i == np.iinfo(np.int64).max).any()  # kOutOfBoundsRecord (ivf_common.cuh:25-31)
     assert (i[:, 0] == np.arange(4)).all()
+
+
+def test_bitset_prefilter_equals_search_over_the_kept_rows():
+    """cuvsFilter{BITSET} (bit = 1 keeps, ids are source ids): same answer as the oracle searching lists from which the
+    filtered rows were removed; no filtered id is ever returned (cpp/tests/neighbors/ann_ivf_flat.cuh filter cases)."""
+    from cuvs_b200.neighbors import filters
+    m = _mod()
+    ds, centers = clustered(12000, 64, 5, n_centers=16)
+    qs, _ = clustered(200, 64, 6, centers=centers)
+    index = m.build(m.IndexParams(n_lists=32, kmeans_n_iters=10), torch.from_numpy(ds).cuda())
+    keep = np.random.default_rng(9).random(12000) < 0.4
+    bits = np.packbits(np.concatenate([keep, np.zeros((-len(keep)) % 32, bool)]), bitorder="little").view(np.uint32)
+    dist, idx = m.search(m.SearchParams(n_probes=8), index, torch.from_numpy(qs).cuda(), 10,
+                         filter=filters.from_bitset(torch.from_numpy(bits.view(np.int32)).cuda()))
+    dist, idx = dist.cpu().numpy(), idx.cpu().numpy()
+    valid = idx != np.iinfo(np.int64).max
+    assert keep[idx[valid]].all(), "a filtered-out row was returned"
+    sizes, ids = _lists_of(index)
+    ids_f = [i[keep[i]] for i in ids]
+    offsets = np.concatenate([[0], np.cumsum([len(i) for i in ids_f])])
+    all_ids = np.concatenate(ids_f)
+    rd, ri = oracle.ivf_flat_search(index.centers.cpu().numpy(), offsets, ds[all_ids], all_ids, qs, 8, 10, "sqeuclidean")
+    assert oracle.recall_with_ties(idx, dist, ri, rd, eps=1e-3) >= 0.999
