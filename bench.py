@@ -373,7 +373,7 @@ class CagraWorkload:
     dtype = "f32"
     timing_section = "cagra_search"
 
-    def __init__(self, n=10_000_000, d=96, nq=10_000, k=10, degree=64, itopk=64, seed=1234, rank=0, world=1):
+    def __init__(self, n=10_000_000, d=96, nq=10_000, k=10, degree=64, itopk=64, seed=1234, rank=0, world=1, walk_bits=16):
         from cuvs_b200.neighbors import brute_force, cagra
         self.n, self.d, self.nq, self.k, self.degree, self.itopk = n, d, nq, k, degree, itopk
         self.name = f"cagra {n // 1_000_000}M x {d} f32, graph_degree={degree} itopk={itopk} search_width=1, batch {nq}, k={k}"
@@ -384,6 +384,9 @@ class CagraWorkload:
         self.index = cagra.build(cagra.IndexParams(graph_degree=degree, intermediate_graph_degree=2 * degree), self.dataset)
         torch.cuda.synchronize()
         self.build_s = time.time() - t0
+        self.walk_bits = walk_bits
+        if walk_bits == 16:
+            self.index.set_walk_precision(16)
         self.sp = cagra.SearchParams(itopk_size=itopk)
         self.h_queries = self.queries.cpu().pin_memory()
         self.neighbors = torch.empty((nq, k), dtype=torch.uint32, device="cuda")
@@ -415,14 +418,17 @@ class CagraWorkload:
 
     def config(self):
         return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
-                "graph_degree": self.degree, "itopk": self.itopk, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "graph_degree": self.degree, "itopk": self.itopk,
+                "walk": "fp16 copy of the rows for the walk + fp32 re-rank of the final 32" if self.walk_bits == 16 else "fp32 rows",
+                "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
                 "data": "rank-16 gaussian manifold in 96-d + 0.05 noise (embedding-like), seeds 1234/4321",
                 "l2_flush": "256 MiB write between timed steps", "parallelism": "single GPU"}
 
     def roofline(self, kernel_ms, pk):
         # upper bound of the walk's traffic: (itopk + iters*degree) vector rows + iters adjacency rows per query
         iters = self.itopk + 5
-        bytes_ub = self.nq * ((self.itopk + self.degree + iters * self.degree) * self.d * 4 + iters * self.degree * 4)
+        row_b = self.d * (2 if self.walk_bits == 16 else 4)  # bytes of one vector row as the walk reads it
+        bytes_ub = self.nq * ((self.itopk + self.degree + iters * self.degree) * row_b + iters * self.degree * 4)
         ach = bytes_ub / (kernel_ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "cagra_search_kernel (one warp per query, register bitonic top-k, smem hash)", "achieved": ach,
                 "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "peak_source": pk["src"] + " HBM copy",
@@ -499,6 +505,7 @@ def run_ours(args):
             kw["itopk"] = args.itopk
         if args.degree:
             kw["degree"] = args.degree
+        kw["walk_bits"] = args.walk_bits
     wl = WORKLOADS[args.workload](**kw)
     res = Resources()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -643,6 +650,8 @@ def main():
     ap.add_argument("--pq-dim", dest="pq_dim", type=int, default=0)
     ap.add_argument("--lut-dtype", dest="lut_dtype", default="f16", choices=["f32", "f16", "u8"],
                     help="ivf_pq search lut_dtype: f16/u8 (reduced-precision LUT, the usual throughput setting) -> 1-pass bf16 scan; f32 (API default) -> 2-pass scan")
+    ap.add_argument("--walk-bits", dest="walk_bits", type=int, default=16, choices=[16, 32],
+                    help="cagra: precision of the rows the graph walk reads (16 = fp16 copy + fp32 re-rank, 32 = fp32)")
     ap.add_argument("--itopk", type=int, default=0)
     ap.add_argument("--degree", type=int, default=0)
     args = ap.parse_args()

@@ -23,6 +23,8 @@
 // Semantics (seeds, hash, parent selection, termination) follow the reference exactly and are
 // restated on the CPU in oracle/oracle.c::oracle_cagra_search.
 #include "common.hpp"
+#include <cuda_fp16.h>
+#include <cuvs_b200/ext.h>
 #include "exact.cuh"
 #include "select_k.cuh"
 #include "timing.hpp"
@@ -51,6 +53,10 @@ struct cagra_index {
   const uint32_t* graph   = nullptr;
   owned<float> data_own;
   owned<uint32_t> graph_own;
+  // Optional fp16 copy of the vectors for the walk (cuvsB200CagraSetWalkPrecision): the walk is bound by random row
+  // gathers from HBM, half-width rows halve its bytes; the returned neighbours are re-ranked with the fp32 rows.
+  owned<__half> data16;
+  int ld16 = 0;  // row pitch in halves (rows padded to 16 bytes)
 };
 
 namespace {
@@ -130,6 +136,8 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&k)[E], int lane)
 }
 
 struct cagra_launch {
+  const __half* data16;  // non-null: the walk reads these rows (pitch ld16), the final list is re-ranked from `data`
+  int ld16;
   const float* data;
   const uint32_t* graph;
   int64_t n;
@@ -177,16 +185,56 @@ __device__ __forceinline__ float team_distance(const float* __restrict__ row, co
   return acc;
 }
 
-__device__ __forceinline__ bool node_kept(const cagra_launch& p, uint32_t id)
+__device__ __forceinline__ bool node_kept(const uint32_t* __restrict__ keep_bits, int64_t n_bits, uint32_t id)
 {
-  return static_cast<int64_t>(id) < p.n_bits && ((p.keep_bits[id >> 5] >> (id & 31)) & 1u);
+  return static_cast<int64_t>(id) < n_bits && ((keep_bits[id >> 5] >> (id & 31)) & 1u);
+}
+
+// the same over an fp16 row (8 halves per 16-byte chunk), accumulated in fp32
+__device__ __forceinline__ float team_distance_h(const __half* __restrict__ row, const float* __restrict__ sq, int dim, int t, bool ip)
+{
+  float acc = 0.f;
+  const int n_chunks = dim >> 3;
+  for (int c = t; c < n_chunks; c += 8) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + c);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float4 q0 = reinterpret_cast<const float4*>(sq)[2 * c], q1 = reinterpret_cast<const float4*>(sq)[2 * c + 1];
+    const float2 x0 = __half22float2(h[0]), x1 = __half22float2(h[1]), x2 = __half22float2(h[2]), x3 = __half22float2(h[3]);
+    if (ip) {
+      acc = fmaf(-q0.x, x0.x, acc); acc = fmaf(-q0.y, x0.y, acc); acc = fmaf(-q0.z, x1.x, acc); acc = fmaf(-q0.w, x1.y, acc);
+      acc = fmaf(-q1.x, x2.x, acc); acc = fmaf(-q1.y, x2.y, acc); acc = fmaf(-q1.z, x3.x, acc); acc = fmaf(-q1.w, x3.y, acc);
+    } else {
+      float d;
+      d = q0.x - x0.x; acc = fmaf(d, d, acc); d = q0.y - x0.y; acc = fmaf(d, d, acc);
+      d = q0.z - x1.x; acc = fmaf(d, d, acc); d = q0.w - x1.y; acc = fmaf(d, d, acc);
+      d = q1.x - x2.x; acc = fmaf(d, d, acc); d = q1.y - x2.y; acc = fmaf(d, d, acc);
+      d = q1.z - x3.x; acc = fmaf(d, d, acc); d = q1.w - x3.y; acc = fmaf(d, d, acc);
+    }
+  }
+  for (int j = (n_chunks << 3) + t; j < dim; j += 8) {
+    const float x = __half2float(row[j]), q = sq[j];
+    if (ip) acc = fmaf(-q, x, acc);
+    else { float df = q - x; acc = fmaf(df, df, acc); }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  return acc;
+}
+
+// (fields passed by value: taking a reference to the __grid_constant__-less kernel parameter struct would force a local copy)
+__device__ __forceinline__ float walk_distance(const __half* data16, int ld16, const float* data, int ld, int dim, uint32_t id,
+                                               const float* __restrict__ sq, int t, bool ip)
+{
+  return data16 ? team_distance_h(data16 + static_cast<int64_t>(id) * ld16, sq, dim, t, ip)
+                : team_distance(data + static_cast<int64_t>(id) * ld, sq, dim, t, ip);
 }
 
 // EI = itopk / 32, EC = (search_width * degree rounded up to 32) / 32 ; buffer = EI + EC keys per lane
 constexpr int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 template <int EI, int EC>
-__global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
+__global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_search_kernel(cagra_launch p)
 {
   constexpr int EB = next_pow2(EI + EC);  // the bitonic network needs a power-of-two key count; spare keys stay ~0 (sort last)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -232,7 +280,7 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
           const uint64_t gid = static_cast<uint64_t>(i) + static_cast<uint64_t>(buf) * static_cast<uint64_t>(j);
           seed               = static_cast<uint32_t>(xorshift64(gid ^ p.rand_xor_mask) % static_cast<uint64_t>(p.n));
         }
-        const float dd = team_distance(p.data + static_cast<int64_t>(seed) * p.ld, sq, p.dim, t, ip);
+        const float dd = walk_distance(p.data16, p.ld16, p.data, p.ld, p.dim, seed, sq, t, ip);
         if (valid_i && dd < best) { best = dd; best_id = seed; }
       }
     }
@@ -274,7 +322,7 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
         const uint32_t pid = __shfl_sync(0xffffffffu, id, src);
         // mark as used; a node the filter rejects may serve as a stepping stone ONCE and then leaves the list
         // (search_single_cta_jit.cuh:297-316: filtered parents are invalidated after their children were expanded)
-        if (lane == src) key[e] = (p.keep_bits != nullptr && !node_kept(p, pid)) ? ~0ull : (key[e] | kMsb);
+        if (lane == src) key[e] = (p.keep_bits != nullptr && !node_kept(p.keep_bits, p.n_bits, pid)) ? ~0ull : (key[e] | kMsb);
         if (lane == 0) sparent[n_parents] = pid;
         ++n_parents;
       }
@@ -309,8 +357,8 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
     for (int c0 = 0; c0 < n_new; c0 += 8) {
       const int ca = c0 + g, cb = c0 + 4 + g;
       const uint32_t ida = ca < n_new ? scand[ca] : 0u, idb = cb < n_new ? scand[cb] : 0u;
-      const float da = team_distance(p.data + static_cast<int64_t>(ida) * p.ld, sq, p.dim, t, ip);
-      const float db = team_distance(p.data + static_cast<int64_t>(idb) * p.ld, sq, p.dim, t, ip);
+      const float da = walk_distance(p.data16, p.ld16, p.data, p.ld, p.dim, ida, sq, t, ip);
+      const float db = walk_distance(p.data16, p.ld16, p.data, p.ld, p.dim, idb, sq, t, ip);
       if (t == 0) {
         if (ca < n_new) sdist[ca] = da;
         if (cb < n_new) sdist[cb] = db;
@@ -332,8 +380,23 @@ __global__ void __launch_bounds__(512) cagra_search_kernel(cagra_launch p)
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
       if (e >= EI) key[e] = ~0ull;
-      else if (key[e] != ~0ull && !node_kept(p, static_cast<uint32_t>(key[e]) & ~kMsb)) key[e] = ~0ull;
+      else if (key[e] != ~0ull && !node_kept(p.keep_bits, p.n_bits, static_cast<uint32_t>(key[e]) & ~kMsb)) key[e] = ~0ull;
     }
+    warp_bitonic_sort<EB>(key, lane);
+  }
+  // ---- fp16 walk: exact fp32 re-rank of the best 32 entries (first register key of every lane), then the usual output
+  if (p.data16 != nullptr) {
+    const uint32_t my_id = key[0] != ~0ull ? (static_cast<uint32_t>(key[0]) & ~kMsb) : kInvalid;
+    float my_d = 0.f;
+    for (int c0 = 0; c0 < 32; c0 += 4) {  // team g scores entry c0 + g
+      const uint32_t id = __shfl_sync(0xffffffffu, my_id, c0 + g);
+      const float d     = team_distance(p.data + static_cast<int64_t>(id == kInvalid ? 0u : id) * p.ld, sq, p.dim, t, ip);
+      const float got   = __shfl_sync(0xffffffffu, d, ((lane - c0) & 3) * 8);  // entry `lane` was scored by team lane - c0
+      if (lane >= c0 && lane < c0 + 4) my_d = got;
+    }
+    if (my_id != kInvalid) key[0] = (static_cast<uint64_t>(dist_key(my_d)) << 32) | (static_cast<uint32_t>(key[0]));
+#pragma unroll
+    for (int e = 1; e < EB; ++e) key[e] = ~0ull;  // only the re-ranked 32 can be returned (k <= 32 in this mode)
     warp_bitonic_sort<EB>(key, lane);
   }
   // ---- results: first k entries of the sorted list
@@ -431,6 +494,7 @@ void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchP
   const int EI = pl.itopk / 32, EC = (n_cand + 31) / 32;
   cagra_launch p{};
   p.data = idx.data; p.graph = idx.graph; p.n = idx.n; p.dim = idx.dim; p.ld = idx.ld; p.degree = idx.degree;
+  p.data16 = (idx.data16.data() != nullptr && k <= 32) ? idx.data16.data() : nullptr; p.ld16 = idx.ld16;
   p.queries = queries; p.nq = nq; p.metric = idx.metric == InnerProduct ? InnerProduct : L2Expanded;
   p.k = k; p.itopk = pl.itopk; p.search_width = w; p.min_iter = pl.min_iter; p.max_iter = pl.max_iter;
   p.hash_bitlen = pl.hash_bitlen; p.small_hash_bitlen = pl.small_hash_bitlen; p.reset_interval = pl.reset_interval;
@@ -461,6 +525,15 @@ void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchP
 }
 
 // ------------------------------------------------------------------ graph build (kNN + reverse edges)
+__global__ void to_half_rows_kernel(const float* __restrict__ x, int64_t n, int dim, int ld, int ld16, __half* __restrict__ out)
+{
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n * ld16) return;
+  const int64_t r = i / ld16;
+  const int c     = static_cast<int>(i % ld16);
+  out[i]          = __float2half_rn(c < dim ? x[r * ld + c] : 0.f);
+}
+
 __global__ void knn_to_graph_kernel(const int64_t* __restrict__ knn, int64_t n, int kk, int keep, uint32_t* __restrict__ graph, int degree)
 {
   // forward half: the `keep` nearest neighbours (self removed)
@@ -973,6 +1046,23 @@ cuvsError_t cuvsCagraSerializeToHnswlib(cuvsResources_t, const char*, cuvsCagraI
 cuvsError_t cuvsCagraMerge(cuvsResources_t, cuvsCagraIndexParams_t, cuvsCagraIndex_t*, size_t, cuvsFilter, cuvsCagraIndex_t)
 {
   return guarded([=] { B2_FAIL("cuvsCagraMerge: graph construction is outside the scan+top-k hot path of this library"); });
+}
+
+/* cuvs_b200 extension (include/cuvs_b200/ext.h): bits = 16 keeps an fp16 copy of the vectors for the graph walk (results are
+ * re-ranked with the fp32 rows); bits = 32 drops it. */
+cuvsError_t cuvsB200CagraSetWalkPrecision(cuvsResources_t res, cuvsCagraIndex_t index, int bits)
+{
+  return guarded([=] {
+    auto r    = as_res(res);
+    auto& idx = cagra_of(index);
+    B2_EXPECTS(bits == 16 || bits == 32, "walk precision must be 16 or 32 bits");
+    if (bits == 32) { idx.data16.release(); idx.ld16 = 0; return; }
+    idx.ld16 = (idx.dim + 7) & ~7;
+    idx.data16.alloc(static_cast<size_t>(idx.n) * idx.ld16);
+    count_launch();
+    to_half_rows_kernel<<<blocks_for(idx.n * idx.ld16, 256), 256, 0, r->stream>>>(idx.data, idx.n, idx.dim, idx.ld, idx.ld16, idx.data16.data());
+    B2_CUDA(cudaGetLastError());
+  });
 }
 
 }  // extern "C"

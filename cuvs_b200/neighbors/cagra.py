@@ -89,6 +89,15 @@ class Index:
     def __len__(self):
         return self._i64(lib.cuvsCagraIndexGetSize)
 
+    def set_walk_precision(self, bits, resources=None):
+        """cuvs_b200 extension: 16 = walk the graph over an fp16 copy of the vectors (half the HBM gather bytes), results
+        re-ranked with the fp32 rows; 32 = exact fp32 walk (default)."""
+        from ..common import Resources
+        res = resources or Resources()
+        check(lib.cuvsB200CagraSetWalkPrecision(res.get_c_obj(), self._p, int(bits)))
+        res.sync()
+        return self
+
     @property
     def graph(self):
         m = DLManagedTensor()

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuvs/core/c_api.h>
 #include <cuvs/neighbors/brute_force.h>
+#include <cuvs/neighbors/cagra.h>
 #include <cuvs/neighbors/ivf_flat.h>
 #ifdef __cplusplus
 extern "C" {
@@ -40,6 +41,11 @@ CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t
 /* Replace the coarse centres of an (empty) index — used by the list-sharded multi-GPU build so that every rank
  * partitions the data with bit-identical centres (trained on one rank, broadcast over NCCL). centers: [n_lists, dim] f32. */
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFlatIndex_t index, DLManagedTensor* centers);
+
+/* CAGRA: the graph walk is bound by random row gathers from HBM.  bits = 16 makes the index keep an fp16 copy of the
+ * vectors that the walk reads instead (half the bytes); the best 32 entries of every query's final list are re-ranked
+ * with the fp32 rows before the k results are returned (k <= 32).  bits = 32 (default) restores the exact fp32 walk. */
+CUVS_EXPORT cuvsError_t cuvsB200CagraSetWalkPrecision(cuvsResources_t res, cuvsCagraIndex_t index, int bits);
 
 #ifdef __cplusplus
 }

@@ -135,3 +135,27 @@ def test_bitset_prefilter_on_a_real_graph():
     kept = np.flatnonzero(keep)
     gd, gi = oracle.knn(ds[kept], qs, 10)
     assert oracle.recall(i, kept[gi]) >= 0.9
+
+
+def test_fp16_walk_reranks_with_fp32_rows():
+    """cuvs_b200 extension: the walk reads an fp16 copy of the rows; returned distances are exact fp32 (re-ranked), ids
+    nearly those of the fp32 walk, recall unchanged."""
+    m = _mod()
+    rng = np.random.default_rng(7)
+    A = (rng.standard_normal((8, 96)) / np.sqrt(8)).astype(np.float32)
+    ds = (rng.standard_normal((20000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((20000, 96)).astype(np.float32))
+    qs = (rng.standard_normal((300, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((300, 96)).astype(np.float32))
+    index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
+    sp = m.SearchParams(itopk_size=64)
+    d32, i32 = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
+    index.set_walk_precision(16)
+    d16, i16 = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
+    i16n, d16n = i16.cpu().numpy().astype(np.int64), d16.cpu().numpy()
+    exact = ((ds[i16n] - qs[:, None, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(d16n, exact, rtol=1e-5, atol=1e-6)           # distances come from the fp32 rows
+    assert (np.diff(d16n, axis=1) >= 0).all()                                # and are sorted after the re-rank
+    gd, gi = oracle.knn(ds, qs, 10)
+    assert oracle.recall(i16n, gi) >= oracle.recall(i32.cpu().numpy().astype(np.int64), gi) - 0.01
+    index.set_walk_precision(32)
+    d_again, i_again = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
+    assert torch.equal(i_again, i32) and torch.equal(d_again, d32)
