@@ -156,6 +156,7 @@ struct cagra_launch {
   uint32_t* out_iters;
   const uint32_t* keep_bits;  // bitset pre-filter over node ids (bit = 1 keeps), null = none
   int64_t n_bits;
+  unsigned long long* work_counter;  // next query index (persistent warps)
 };
 
 // squared L2 / negative dot between the smem query and a dataset row, computed by a team of 8 lanes
@@ -238,8 +239,7 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
 {
   constexpr int EB = next_pow2(EI + EC);  // the bitonic network needs a power-of-two key count; spare keys stay ~0 (sort last)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t qi = static_cast<int64_t>(blockIdx.x) * warps + wid;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool ip    = p.metric == InnerProduct;
   const int qpad   = (p.dim + 3) & ~3;
   const uint32_t small_size = p.small_hash_bitlen ? (1u << p.small_hash_bitlen) : 0u;
@@ -252,7 +252,14 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
   uint32_t* scand       = shash + small_size;
   float* sdist          = reinterpret_cast<float*>(scand + EB * 32);
   uint32_t* sparent     = reinterpret_cast<uint32_t*>(sdist + EB * 32);
-  if (qi >= p.nq) return;
+  // Persistent warps: every warp keeps pulling queries from a global counter until the batch is drained.  Walks differ in
+  // length, and a batch is only ~1.4 "waves" of resident warps: with one query per warp and CTA-granular scheduling the
+  // early finishers idle and the second wave runs nearly empty.
+  for (;;) {
+  int64_t qi = 0;
+  if (lane == 0) qi = static_cast<int64_t>(atomicAdd(p.work_counter, 1ull));
+  qi = __shfl_sync(0xffffffffu, qi, 0);
+  if (qi >= p.nq) break;
 
   const uint32_t bitlen = p.small_hash_bitlen ? p.small_hash_bitlen : p.hash_bitlen;
   uint32_t* table       = p.small_hash_bitlen ? shash : p.hash_global + (static_cast<size_t>(qi) << p.hash_bitlen);
@@ -414,6 +421,8 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
     }
   }
   if (p.out_iters && lane == 0) p.out_iters[qi] = iter + 1;
+  __syncwarp();
+  }  // next query
 }
 
 struct cagra_plan {
@@ -473,9 +482,18 @@ void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
   const size_t smem = per_warp_smem * warps;
   B2_EXPECTS(per_warp_smem <= 200 * 1024, "cagra search: per-query shared memory (%zu bytes) exceeds the limit", per_warp_smem);
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 1, dev = 0, sms = 148;
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = std::min<unsigned>(blocks_for(p.nq, warps), static_cast<unsigned>(std::max(per_sm, 1) * sms));
+  dbuf<unsigned long long> counter(1, s);
+  B2_CUDA(cudaMemsetAsync(counter.data(), 0, sizeof(unsigned long long), s));
+  cagra_launch pl = p;
+  pl.work_counter = counter.data();
   timed_section ts("cagra_search", s);
   count_launch();
-  kern<<<blocks_for(p.nq, warps), warps * 32, smem, s>>>(p);
+  kern<<<grid, warps * 32, smem, s>>>(pl);
   B2_CUDA(cudaGetLastError());
 }
 
