@@ -451,7 +451,105 @@ class CagraWorkload:
                 "sample": f"{m} of {self.nq} queries, exact fp32 kNN over all {self.n} rows (oracle/oracle.c, OpenMP)"}
 
 
-WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "cagra": CagraWorkload}
+class IvfFlatWorkload:
+    """configs[4] scaled to what builds in-bench: ivf_flat::search n x 128 f32 (default 10M), sharded by IVF list over the
+    ranks (list % world) with one NCCL all-gather of the partial top-k (cuvs_b200/distributed.py)."""
+    dtype = "bf16 tensor-core list scan (1 pass), fp32 accumulate; exact fp32 re-score of the candidates"
+    timing_section = "ivf_flat_scan"
+
+    def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=4096, n_probes=64, seed=1234, rank=0, world=1):
+        from cuvs_b200.neighbors import ivf_flat
+        from cuvs_b200.distributed import ShardedIvfFlat, build_sharded_ivf_flat
+        self.n, self.d, self.nq, self.k, self.n_lists, self.n_probes = n, d, nq, k, n_lists, n_probes
+        self.rank, self.world = rank, world
+        self.name = f"ivf_flat {n // 1_000_000}M x {d} f32, n_lists={n_lists} n_probes={n_probes}, batch {nq}, k={k}"
+        self.flat = ivf_flat
+        self.dataset = gen_manifold(n, d, seed)
+        self.queries = gen_manifold(nq, d, seed + 3087)
+        t0 = time.time()
+        params = ivf_flat.IndexParams(n_lists=n_lists, kmeans_n_iters=10, kmeans_trainset_fraction=min(0.5, max(2_000_000, 128 * n_lists) / n))
+        if world == 1:
+            self.index = ivf_flat.build(params, self.dataset)
+            self.sharded = None
+        else:
+            step = 1 << 21
+            ids = torch.arange(n, dtype=torch.int64, device="cuda")
+            chunks = ((self.dataset[s:s + step], ids[s:s + step]) for s in range(0, n, step))
+            n_train = int(max(2_000_000, 128 * n_lists))
+            self.sharded = build_sharded_ivf_flat(params, self.dataset[:: max(1, n // n_train)].contiguous(), chunks)
+            self.index = self.sharded.local
+        torch.cuda.synchronize()
+        self.build_s = time.time() - t0
+        self.sp = ivf_flat.SearchParams(n_probes=n_probes)
+        self.h_queries = self.queries.cpu().pin_memory()
+        self.neighbors = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        self.gt = exact_ground_truth(self.dataset, self.queries, k)
+        self.recall = None
+
+    def _search(self, q, res):
+        if self.sharded is not None:
+            self.final_d, self.final_i = self.sharded.search(self.sp, q, self.k, resources=res)
+        else:
+            self.flat.search(self.sp, self.index, q, self.k, neighbors=self.neighbors, distances=self.distances, resources=res)
+            self.final_d, self.final_i = self.distances, self.neighbors
+
+    def step(self, res):
+        self._search(self.queries, res)
+
+    def e2e_step(self, res):
+        q = self.h_queries.to("cuda", non_blocking=True)
+        self._search(q, res)
+        self.h_neighbors.copy_(self.final_i, non_blocking=True)
+        self.h_distances.copy_(self.final_d, non_blocking=True)
+
+    def e2e_bytes(self):
+        return self.nq * self.d * 4, self.nq * self.k * 12
+
+    def units(self):
+        return self.nq
+
+    def check(self):
+        self.recall = (self.final_i.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
+        return self.recall >= 0.95
+
+    def config(self):
+        return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
+                "n_lists": self.n_lists, "n_probes": self.n_probes, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "data": "rank-16 gaussian manifold in 128-d + 0.05 noise (embedding-like), seeds 1234/4321",
+                "l2_flush": "256 MiB write between timed steps",
+                "parallelism": "single GPU" if self.world == 1 else
+                f"index sharded by IVF list over {self.world} GPUs (list % {self.world}), per-shard scan + exact re-score, one NCCL "
+                "all-gather of partial top-k + k-way merge on every rank"}
+
+    def roofline(self, kernel_ms, pk):
+        # scanned (query, row) pairs of THIS rank (lists it owns), from the probe lists the library itself would compute
+        c = self.flat_centers()
+        sizes = self.index.list_sizes.to(torch.int64)
+        rows = 0
+        for s in range(0, self.nq, 2048):
+            q = self.queries[s:s + 2048]
+            dist = (c * c).sum(1)[None, :] - 2.0 * q @ c.t()
+            rows += int(sizes[dist.topk(self.n_probes, dim=1, largest=False).indices].sum().item())
+        flops = 2.0 * rows * self.d
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "tc_scan_kernel over IVF-Flat lists (tcgen05 bf16 1-pass, fused top-k')", "achieved": ach,
+                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "traffic": None, "kernel_ms": kernel_ms,
+                "scanned_rows": rows,
+                "reference_formulation": {"algorithmic_bytes": rows * self.d * 4,
+                                          "note": "the reference re-reads list_len*dim*4 bytes per (query, probe) pair (SURVEY a8)"}}
+
+    def flat_centers(self):
+        return self.index.centers
+
+    def cpu_baseline(self, budget_s=20.0):
+        return IvfPqWorkload.cpu_baseline(self, budget_s)
+
+
+WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "cagra": CagraWorkload, "ivf_flat": IvfFlatWorkload}
 
 
 METRIC_NAME = "QPS @ recall@10>=0.95 (queries/s of one batched 10k-query search() call; recall@10 in config)"
@@ -497,6 +595,11 @@ def run_ours(args):
     if args.workload == "ivf_pq":
         kw["lut_dtype"] = args.lut_dtype
         for name in ("n_lists", "n_probes", "refine_ratio", "pq_dim"):
+            if getattr(args, name):
+                kw[name] = getattr(args, name)
+        kw["rank"], kw["world"] = rank, world
+    if args.workload == "ivf_flat":
+        for name in ("n_lists", "n_probes"):
             if getattr(args, name):
                 kw[name] = getattr(args, name)
         kw["rank"], kw["world"] = rank, world
@@ -595,17 +698,19 @@ def run_reference(args):
     import oracle
     oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     wl = args.workload
-    n = args.n or (10_000_000 if wl == "ivf_pq" else 1_000_000)
+    n = args.n or (10_000_000 if wl in ("ivf_pq", "ivf_flat", "cagra") else 1_000_000)
     d, nq, k = 128, args.nq or 10_000, 10
     rng = np.random.default_rng(1234)
-    if wl == "ivf_pq":
+    if wl in ("ivf_pq", "ivf_flat", "cagra"):
+        if wl == "cagra":
+            d = 96
         A = (np.random.default_rng(99).standard_normal((16, d)) / 4.0).astype(np.float32)
         ds = np.empty((n, d), np.float32)
         for s0 in range(0, n, 1 << 20):
             e = min(n, s0 + (1 << 20))
             ds[s0:e] = rng.standard_normal((e - s0, 16), dtype=np.float32) @ A + 0.05 * rng.standard_normal((e - s0, d), dtype=np.float32)
         qs = (rng.standard_normal((256, 16), dtype=np.float32) @ A + 0.05 * rng.standard_normal((256, d), dtype=np.float32)).astype(np.float32)
-        name = f"ivf_pq {n // 1_000_000}M x {d} f32 workload, answered by exact CPU kNN (the reference has no CPU IVF-PQ)"
+        name = f"{wl} {n // 1_000_000}M x {d} f32 workload, answered by exact CPU kNN (the reference has no CPU {wl} search)"
     else:
         centers = np.random.default_rng(99).standard_normal((max(1, n // 1000), d)).astype(np.float32)
         ds = (centers[rng.integers(0, len(centers), n)] + 0.25 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
