@@ -69,38 +69,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
   while (!mbar_try_wait(bar, parity)) {}
 }
 
-// experiment variants of the wait: no suspend-time hint (plain polling), or a caller-chosen hint
-__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity)
-{
-  uint32_t ok;
-  do {
-    asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns)
-{
-  uint32_t ok;
-  do {
-    asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  } while (!ok);
-}
-
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m)
 {

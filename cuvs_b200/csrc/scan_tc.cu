@@ -233,9 +233,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         ptx::tc_fence_after_sync();
       }
       for (uint32_t t = 0; t < n_tiles; ++t) {
-        if (dbg_flags & 32) ptx::mbar_wait_poll(&tempty[acc], acc_phase ^ 1);
-        else if (dbg_flags & 64) ptx::mbar_wait_hint(&tempty[acc], acc_phase ^ 1, 1000);
-        else ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * 128;
 #pragma unroll
@@ -294,9 +292,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     // One tile: wait for the accumulator, pull this thread's 64 columns into registers, hand the TMEM buffer back.
     auto fetch_tile = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
-      if (dbg_flags & 16) ptx::mbar_wait_poll(&tfull[acc], acc_phase);
-      else if (dbg_flags & 64) ptx::mbar_wait_hint(&tfull[acc], acc_phase, 1000);
-      else ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after_sync();
       ptx::tmem_ld_32x32(t_lane + acc * 128, v0);
       ptx::tmem_ld_32x32(t_lane + acc * 128 + 32, v1);
@@ -510,7 +506,8 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
   // profiling knob: MMA/TMA pipeline only (results are garbage); only honoured inside a timed region (cuvsB200TimingEnable)
   static const int skip_env = env_int("CUVS_B200_TC_SKIP_EPI", 0);
   static const int no_pf    = env_int("CUVS_B200_TC_PREFETCH", 0) ? 0 : 1;  // L2 prefetch of the B stream: measured no gain, off
-  const int skip_epi        = (skip_env && timing_enabled() ? (skip_env & 0xf71) : 0) | (no_pf ? 2 : 0);  // 1 skip scan, 4 skip LDTM, 8 x64 LDTM
+  // bit 0: skip the top-k work; bits 8..11: smem ring depth override (both only for the limiter experiments of profiles/README.md)
+  const int skip_epi        = (skip_env && timing_enabled() ? (skip_env & 0xf01) : 0) | (no_pf ? 2 : 0);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
