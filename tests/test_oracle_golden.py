@@ -113,3 +113,17 @@ def test_ivf_flat_interleave_layout():
     for r, k in [(0, 0), (5, 3), (5, 4), (33, 7)]:
         off = (r // 32) * 32 * 8 + (k // veclen) * 32 * veclen + (r % 32) * veclen + k % veclen
         assert flat[off] == rows[r, k]
+
+
+def test_blocked_gemm_formulation_agrees_with_the_pinned_scan():
+    """oracle.knn_blocked (SGEMM + top-k, the throughput formulation used as bench.py's CPU baseline) returns the same
+    neighbours as oracle.knn (sequential fmaf chains, the parity checker) up to last-ulp rounding of the expanded form."""
+    rng = np.random.default_rng(11)
+    ds = rng.standard_normal((30000, 48)).astype(np.float32)
+    qs = rng.standard_normal((300, 48)).astype(np.float32)
+    for metric in ("sqeuclidean", "inner_product"):
+        d0, i0 = oracle.knn(ds, qs, 7, metric)
+        d1, i1 = oracle.knn_blocked(ds, qs, 7, metric, rows_per_block=7000, queries_per_block=128)
+        assert oracle.recall_with_ties(i1, d1, i0, d0, eps=1e-3) >= 0.9999
+        assert (i0 == i1).mean() >= 0.999
+        np.testing.assert_allclose(d1, d0, rtol=1e-4, atol=2e-4)
