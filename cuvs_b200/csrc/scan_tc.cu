@@ -508,11 +508,9 @@ void launch(cudaStream_t stream, int sm_count, const CUtensorMap& a_hi, const CU
   static const int no_pf    = env_int("CUVS_B200_TC_PREFETCH", 0) ? 0 : 1;  // L2 prefetch of the B stream: measured no gain, off
   // bit 0: skip the top-k work; bits 8..11: smem ring depth override (both only for the limiter experiments of profiles/README.md)
   const int skip_epi        = (skip_env && timing_enabled() ? (skip_env & 0xf01) : 0) | (no_pf ? 2 : 0);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
-    attr_set = true;
-  }
+  // per launch, not once: the attribute belongs to the current device's context, and one process may drive several GPUs
+  // (cuvsMultiGpu*); the call costs about a microsecond
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem)));
   int grid = n_items < sm_count ? n_items : sm_count;
   dbuf<int> sched;  // the kernel's work-item counter
   if (dynamic) {
