@@ -118,3 +118,17 @@ def test_product_never_imports_the_oracle():
             if re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M) or "liboracle" in txt:
                 bad.append(f)
     assert not bad, bad
+
+
+def test_plain_c_client_compiles_links_and_runs_without_a_gpu(tmp_path):
+    """examples/c/ivf_pq_search.c uses only the reference's C API (what a cgo / JNI / bindgen binding calls): it must
+    compile as C against include/, link against the in-tree libcuvs_c.so and run its GPU-free path."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "ivf_pq_search"
+    cmd = ["/usr/bin/gcc", os.path.join(root, "examples", "c", "ivf_pq_search.c"), "-I" + os.path.join(root, "include"),
+           "-I/usr/local/cuda/include", "-L" + os.path.join(root, "cuvs_b200", "lib"), "-lcuvs_c", "-L/usr/local/cuda/lib64",
+           "-lcudart", "-Wl,-rpath," + os.path.join(root, "cuvs_b200", "lib"), "-Wall", "-Werror", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe), "--version"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("libcuvs_c 26."), out.stdout + out.stderr
