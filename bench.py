@@ -11,6 +11,12 @@ A step = one search() of the whole 10k-query batch through the library's C ABI.
   cpu_baseline  the oracle (C port, OpenMP) on a bounded sample of the same workload, rank 0, N=1
 --impl reference: the reference has no CPU implementation of these searches and its CUDA build
 cannot be produced offline, so the reference arm times the oracle port on the host cores.
+
+Workloads (--workload): ivf_pq (default; BASELINE configs[2]: 10M x 128, n_lists 1024, pq_dim 64, n_probes 64, exact refine of
+2k candidates; --lut-dtype f16|u8|f32; N > 1 = index sharded by IVF list, one all-gather of partial top-k), brute_force
+(configs[1], 1M x 128, bit-exact vs the oracle), cagra (configs[3], 10M x 96, degree 64, itopk 64; --walk-bits 16|32), ivf_flat
+(configs[4] scaled to 10M, list-sharded for N > 1).  The headline 100M x 128 shape: --n 100000000 --n-lists 16384 --n-probes 48
+(51 GB of vectors on the device; not part of the default run).  --no-cpu skips the CPU baseline.
 """
 from __future__ import annotations
 
