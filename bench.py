@@ -12,11 +12,13 @@ A step = one search() of the whole 10k-query batch through the library's C ABI.
 --impl reference: the reference has no CPU implementation of these searches and its CUDA build
 cannot be produced offline, so the reference arm times the oracle port on the host cores.
 
-Workloads (--workload): ivf_pq (default; BASELINE configs[2]: 10M x 128, n_lists 1024, pq_dim 64, n_probes 64, exact refine of
-2k candidates; --lut-dtype f16|u8|f32; N > 1 = index sharded by IVF list, one all-gather of partial top-k), brute_force
-(configs[1], 1M x 128, bit-exact vs the oracle), cagra (configs[3], 10M x 96, degree 64, itopk 64; --walk-bits 16|32), ivf_flat
-(configs[4] scaled to 10M, list-sharded for N > 1).  The headline 100M x 128 shape: --n 100000000 --n-lists 16384 --n-probes 48
-(51 GB of vectors on the device; not part of the default run).  --no-cpu skips the CPU baseline.
+Workloads (--workload): ivf_pq (DEFAULT = the metric's configuration: 100M x 128 f32 on one GPU, n_lists 16384, pq_dim 64 (64-byte
+codes), n_probes 48, exact refine of 2k candidates, batch 10k, k 10; 51 GB of vectors generated on the device; --lut-dtype
+f16|u8|f32; N > 1 = index sharded by IVF list, one all-gather of partial top-k), ivf_pq_c2 (BASELINE configs[2]: 10M x 128, n_lists
+1024, n_probes 64), brute_force (configs[1], 1M x 128, bit-exact vs the oracle), cagra (configs[3], 10M x 96, degree 64, itopk 64;
+--walk-bits 32|16), ivf_flat (configs[4] scaled to 10M, list-sharded for N > 1).  --no-cpu skips the CPU baseline, --no-aux the
+secondary harder-data point.  Recall denominators come from our exact brute force, itself checked against the oracle on a slice
+of the same tensors (config.ground_truth_check); a failed check or recall < 0.95 adds PARITY_FAILED to the line.
 """
 from __future__ import annotations
 
@@ -168,8 +170,7 @@ class BruteForceWorkload:
                 "traffic": None, "kernel_ms": kernel_ms}
 
     def cpu_baseline(self, budget_s=20.0):
-        return cpu_exact_knn_rate(self.dataset.cpu().numpy(), self.queries[:1024].cpu().numpy(), self.k, budget_s,
-                                  "the same search, answered on the host")
+        return cpu_baseline_on_slice(self.dataset, self.queries, self.k, budget_s, "the same search, answered on the host")
 
     def check(self):
         import oracle
@@ -179,33 +180,76 @@ class BruteForceWorkload:
         return bool(ok)
 
 
-def cpu_exact_knn_rate(ds, qs, k, budget_s, what):
-    """CPU baseline: exact kNN over `ds` (host numpy) on all host threads, with whichever of the oracle's two formulations
-    is faster on this machine — sequential-fmaf scan (oracle.knn, the parity checker) or blocked SGEMM + top-k
-    (oracle.knn_blocked) — measured on a bounded sample sized to ~budget_s seconds."""
-    import oracle
+def cpu_exact_knn_rate(ds_rows, qs, k, budget_s, what, n_total=None):
+    """CPU baseline: exact fp32 kNN with the oracle port on ALL host threads, in a separate process with pinned OpenMP
+    threads (oracle/cpu_baseline.py), 3 timed repeats after a warm-up, median reported.  `ds_rows` may be a ROW SLICE of the
+    workload's dataset (host RAM / time bound): the rate is then scaled by rows(slice) / n_total — exact kNN cost is linear
+    in the rows scanned — and the sample says so."""
+    import tempfile
     threads = os.cpu_count() or 1
-    oracle.set_threads(threads)  # torchrun exports OMP_NUM_THREADS=1
-    n = ds.shape[0]
+    n_slice = ds_rows.shape[0]
+    n_total = n_total or n_slice
+    tag = f"cuvs_b200_cpu_{os.getpid()}"
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    f_ds, f_q = os.path.join(shm, tag + "_ds.npy"), os.path.join(shm, tag + "_q.npy")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads", MKL_NUM_THREADS=str(threads))
+    script = os.path.join(ROOT, "oracle", "cpu_baseline.py")
+    try:
+        np.save(f_ds, ds_rows)
+        # size the query sample from a short probe run so that warm-up + 3 repeats take ~budget_s
+        np.save(f_q, np.ascontiguousarray(qs[:16]))
+        r = subprocess.run([sys.executable, script, f_ds, f_q, str(k), "1"], env=env, capture_output=True, text=True, timeout=600)
+        probe = json.loads(r.stdout.strip().splitlines()[-1])
+        rate = max(probe["probe_rates_qps"].values())
+        m = int(max(16, min(len(qs), budget_s / 4.0 * rate)))
+        np.save(f_q, np.ascontiguousarray(qs[:m]))
+        r = subprocess.run([sys.executable, script, f_ds, f_q, str(k), "3", probe["formulation"]], env=env, capture_output=True,
+                           text=True, timeout=900)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    finally:
+        for f in (f_ds, f_q):
+            if os.path.exists(f):
+                os.remove(f)
+    ts = sorted(out["times_s"])
+    scale = n_slice / float(n_total)
+    qps = [m / t * scale for t in ts]
+    form = "blocked SGEMM + top-k (oracle.knn_blocked)" if out["formulation"] == "blocked" else "sequential-fmaf scan (oracle.knn, OpenMP)"
+    sample = (f"{m} queries, exact fp32 kNN over {n_slice} rows"
+              + (f" (a row slice of the {n_total}-row dataset; rate scaled by {scale:.4g}: cost is linear in rows)" if n_slice != n_total else "")
+              + f" ({what}); {form}; separate process, OMP_PROC_BIND=spread OMP_PLACES=threads; 3 repeats after warm-up: "
+              f"median {qps[1]:.3g}, min {qps[-1]:.3g}, max {qps[0]:.3g} q/s")
+    return {"value": qps[1], "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample,
+            "repeats_qps": qps}
+
+
+CPU_SLICE_ROWS = 4_000_000   # rows of the dataset the CPU arms scan (host RAM / time bound); rates are scaled to the full size
+GT_CHECK_ROWS = 1_000_000    # rows over which the ground-truth machinery is checked against the oracle
+GT_CHECK_QUERIES = 256
+
+
+def cpu_baseline_on_slice(dataset, queries, k, budget_s, what):
+    n = dataset.shape[0]
+    m = min(n, CPU_SLICE_ROWS)
+    return cpu_exact_knn_rate(dataset[:m].cpu().numpy(), queries[:1024].cpu().numpy(), k, budget_s, what, n_total=n)
+
+
+def oracle_gt_check(dataset, queries, k):
+    """The recall denominators of the IVF / graph workloads come from our own exact brute force (the only thing that can
+    answer 10k queries over 1e8 rows here).  This pins that machinery to the ORACLE on the same tensors: exact kNN of the
+    first 256 queries over the first 1M rows by `oracle.knn` (CPU, pinned fp32 arithmetic) vs `exact_ground_truth` on the
+    same slice — ids must agree (bit-exact brute force; a handful of exact-tie swaps are tolerated)."""
+    import oracle
+    oracle.set_threads(os.cpu_count() or 1)
+    rows = min(dataset.shape[0], GT_CHECK_ROWS)
+    nq = min(queries.shape[0], GT_CHECK_QUERIES)
+    ds, qs = dataset[:rows], queries[:nq]
     t0 = time.time()
-    oracle.knn(ds, qs[:4], k)
-    r_scan = 4 / max(time.time() - t0, 1e-9)
-    probe = min(64, len(qs))
-    t0 = time.time()
-    oracle.knn_blocked(ds, qs[:probe], k, threads=threads)
-    r_blk = probe / max(time.time() - t0, 1e-9)
-    use_blk = r_blk > r_scan
-    m = int(max(8, min(len(qs), budget_s * max(r_blk, r_scan))))
-    t0 = time.time()
-    if use_blk:
-        oracle.knn_blocked(ds, qs[:m], k, threads=threads)
-    else:
-        oracle.knn(ds, qs[:m], k)
-    dt = time.time() - t0
-    return {"value": m / dt, "unit": "queries/s", "cores": threads, "kind": "port",
-            "sample": f"{m} queries, exact fp32 kNN over all {n} rows ({what}); formulation: "
-                      + ("blocked SGEMM + top-k (oracle.knn_blocked)" if use_blk else "sequential-fmaf scan (oracle.knn, OpenMP)")
-                      + f"; probe rates scan {r_scan:.1f} q/s, blocked {r_blk:.1f} q/s"}
+    _, ri = oracle.knn(ds.cpu().numpy(), qs.cpu().numpy(), k)
+    ours = exact_ground_truth(ds, qs.contiguous(), k).cpu().numpy()
+    same = float((ours == ri).mean())
+    sets = float(np.mean([len(np.intersect1d(a, b)) / float(k) for a, b in zip(ours, ri)]))
+    return {"queries": int(nq), "rows": int(rows), "ids_identical": same, "id_sets_identical": sets, "ok": bool(sets >= 0.999),
+            "checker": "oracle.knn (CPU)", "seconds": round(time.time() - t0, 1)}
 
 
 def exact_ground_truth(dataset, queries, k, chunk=10_000_000):
@@ -227,21 +271,24 @@ def exact_ground_truth(dataset, queries, k, chunk=10_000_000):
 
 
 class IvfPqWorkload:
-    """configs[2]: ivf_pq::search 10M x 128 f32, nlist=1024 pq_dim=64 nprobe=64, batch 10k (+ exact refine to reach recall)."""
-    dtype = "bf16 tensor-core scan of decoded PQ rows, fp32 accumulate; fp32 exact refine"
+    """The metric's configuration: ivf_pq::search 100M x 128 f32 on one B200, batch 10k, k=10 (n_lists 16384, pq_dim 64 ->
+    64-byte codes, the smallest n_probes with recall@10 >= 0.95 after an exact refine of 2k candidates).  BASELINE configs[2]
+    (10M x 128, n_lists 1024, n_probes 64) is `--workload ivf_pq_c2`."""
+    dtype = "bf16 (PQ codes decoded to bf16 on the SM, tcgen05 bf16 MMA, fp32 accumulate); fp32 exact refine"
     timing_section = "pq_scan"
 
-    def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=1024, pq_dim=64, n_probes=64, refine_ratio=2, seed=1234,
-                 rank=0, world=1, lut_dtype="f16"):
+    def __init__(self, n=100_000_000, d=128, nq=10_000, k=10, n_lists=16384, pq_dim=64, n_probes=48, refine_ratio=2, seed=1234,
+                 rank=0, world=1, lut_dtype="f16", data_rank=16):
         from cuvs_b200.neighbors import brute_force, ivf_pq, refine
         self.n, self.d, self.nq, self.k = n, d, nq, k
         self.rank, self.world = rank, world
         self.n_lists, self.pq_dim, self.n_probes, self.refine_ratio = n_lists, pq_dim, n_probes, refine_ratio
+        self.data_rank = data_rank
         self.name = (f"ivf_pq {n // 1_000_000}M x {d} f32, n_lists={n_lists} pq_dim={pq_dim} pq_bits=8 n_probes={n_probes}, "
                      f"batch {nq}, k={k}, refine_ratio={refine_ratio}")
         self.pq, self.refine = ivf_pq, refine
-        self.dataset = gen_manifold(n, d, seed)
-        self.queries = gen_manifold(nq, d, seed + 3087)
+        self.dataset = gen_manifold(n, d, seed, rank=data_rank)
+        self.queries = gen_manifold(nq, d, seed + 3087, rank=data_rank)
         t0 = time.time()
         params = ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10,
                                     kmeans_trainset_fraction=min(0.5, max(4_000_000, 256 * n_lists) / n))
@@ -264,8 +311,9 @@ class IvfPqWorkload:
         self.distances = torch.empty((nq, k), dtype=torch.float32, device="cuda")
         self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
         self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-        # ground truth (exact, our brute force) for recall
+        # ground truth (exact, our brute force — itself pinned to the oracle on a slice of these tensors) for recall
         self.gt = exact_ground_truth(self.dataset, self.queries, k)
+        self.gt_check = oracle_gt_check(self.dataset, self.queries, k) if rank == 0 else None
         self.recall = None
 
     def _build_shard(self, params):
@@ -333,7 +381,7 @@ class IvfPqWorkload:
         nb = self.final_i if self.sharded is not None else self.neighbors
         hit = (nb.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
         self.recall = hit
-        return hit >= 0.95
+        return hit >= 0.95 and (self.gt_check is None or self.gt_check["ok"])
 
     def config(self):
         sizes = self.index.list_sizes.float()
@@ -342,42 +390,65 @@ class IvfPqWorkload:
                 "refine_ratio": self.refine_ratio, "lut_dtype": self.lut_dtype,
                 "scan": ("2-pass split-bf16 residual x bf16-exact decoded rows = the fp32 LUT sums to fp32 rounding" if self.lut_dtype == "f32"
                          else "1-pass bf16 residual x decoded rows (reduced-precision LUT requested)"),
-                "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "scan_kernel": "pq_stream_scan_kernel: 64-byte codes streamed from HBM, decoded on the SM (scan_pq.cu)",
+                "recall_at_10": self.recall, "ground_truth_check": self.gt_check, "index_build_s": round(self.build_s, 2),
                 "list_size_max_over_mean": round((sizes.max() / sizes.mean()).item(), 2),
-                "data": "rank-16 gaussian manifold in 128-d + 0.05 noise (embedding-like), seeds 1234/4321",
+                "index_device_bytes": self.index.device_bytes, "index_streamed": self.index.streamed,
+                "data": f"rank-{self.data_rank} gaussian manifold in {self.d}-d + 0.05 noise (embedding-like), seeds 1234/4321; "
+                        "SURVEY 8d's clustered gaussians (sigma 0.25: 1000 near-equidistant neighbours per point) make recall@10 a coin "
+                        "toss for any PQ/graph method and are used for brute_force only; `harder_data` below = the same run on rank-32 data",
                 "l2_flush": "256 MiB write between timed steps",
                 "parallelism": "single GPU" if self.world == 1 else
                 f"index sharded by IVF list over {self.world} GPUs (list % {self.world}), per-shard search + exact refine, one NCCL "
                 "all-gather of partial top-k + k-way merge on every rank"}
 
-    def scanned_rows(self):
-        """sum over (query, probe) pairs of the probed list's length (algorithmic scan volume)."""
+    def scan_volume(self):
+        """(sum over (query, probe) pairs of the probed list's length, padded rows of the DISTINCT probed lists) — from the
+        probe sets the library itself would compute (lists owned by other ranks have size 0 here)."""
         c = self.index.centers
-        sizes = self.index.list_sizes.to(torch.int64)  # lists owned by other ranks have size 0 here
+        sizes = self.index.list_sizes.to(torch.int64)
+        touched = torch.zeros(self.n_lists, dtype=torch.bool, device="cuda")
         tot = 0
         for s in range(0, self.nq, 2048):
             q = self.queries[s:s + 2048]
             dist = (c * c).sum(1)[None, :] - 2.0 * q @ c.t()
             pr = dist.topk(self.n_probes, dim=1, largest=False).indices
             tot += int(sizes[pr].sum().item())
-        return tot
+            touched[pr.reshape(-1)] = True
+        padded = ((sizes + 127) // 128 * 128)[touched & (sizes > 0)]
+        return tot, int(padded.sum().item())
 
     def roofline(self, kernel_ms, pk):
-        rows = self.scanned_rows()
-        flops = 2.0 * rows * self.d  # one multiply-add per (pair, row, component)
-        code_bytes = rows * self.pq_dim  # bytes of PQ codes the reference formulation streams (one read per pair)
-        ach = flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "tc_scan_kernel over decoded PQ rows (tcgen05 bf16, fused top-k')", "achieved": ach,
-                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "traffic": None, "kernel_ms": kernel_ms,
-                "scanned_rows": rows,
-                "reference_formulation": {"algorithmic_code_bytes": code_bytes,
-                                          "equivalent_GBps": code_bytes / (kernel_ms * 1e-3) / 1e9,
-                                          "frac_of_hbm_peak": code_bytes / (kernel_ms * 1e-3) / 1e9 / pk["hbm"]}}
+        """Dominant kernel = the fine scan.  Two ceilings, both from ALGORITHMIC work:
+        hbm    every probed list's code stream read once: (pq_dim + 4) bytes per (padded) row of the distinct probed lists
+               — the compulsory traffic of a batch (at 100M rows every list is probed by some query of a 10k batch);
+        tensor one multiply-add per (query-probe pair, list row, component): 2 * scanned_rows * dim FLOP.
+        `bound` names the ceiling the launch sits closer to; `frac` is against it."""
+        rows, touched_rows = self.scan_volume()
+        flops = 2.0 * rows * self.d
+        hbm_bytes = touched_rows * (self.pq_dim + 4.0)
+        t = kernel_ms * 1e-3
+        tf, gbs = flops / t / 1e12, hbm_bytes / t / 1e9
+        f_t, f_h = tf / pk["tf_burst"], gbs / pk["hbm"]
+        kern = ("pq_stream_scan_kernel (PQ codes streamed by cp.async.bulk, decoded on the SM, tcgen05 bf16 MMA, threshold "
+                "filter epilogue)" if getattr(self.index, "streamed", True) else "tc_scan_kernel over decoded PQ rows")
+        out = {"kernel": kern, "kernel_ms": kernel_ms, "scanned_rows": rows, "touched_list_rows": touched_rows,
+               "algorithmic_hbm_bytes": hbm_bytes, "algorithmic_flops": flops, "traffic": None,
+               "hbm": {"achieved_GBps": gbs, "peak_GBps": pk["hbm"], "frac": f_h},
+               "tensor": {"achieved_TFLOPs": tf, "peak_TFLOPs": pk["tf_burst"], "frac": f_t},
+               "peak_source": pk["src"] + " (HBM copy bandwidth; bf16 burst: the kernel is timed alone)",
+               "reference_formulation": {"algorithmic_code_bytes": rows * self.pq_dim,
+                                         "note": "the reference streams list_len * pq_dim code bytes per (query, probe) pair; this kernel "
+                                                 "streams each probed list once per group of <= 64 probing queries"}}
+        if f_h >= f_t:
+            out.update({"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": f_h})
+        else:
+            out.update({"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": f_t})
+        return out
 
     def cpu_baseline(self, budget_s=20.0):
-        return cpu_exact_knn_rate(self.dataset.cpu().numpy(), self.queries[:1024].cpu().numpy(), self.k, budget_s,
-                                  "the reference has no CPU IVF / graph search; exact kNN is its CPU answer")
+        return cpu_baseline_on_slice(self.dataset, self.queries, self.k, budget_s,
+                                     "the reference has no CPU IVF / graph search; exact kNN is its CPU answer")
 
 
 class CagraWorkload:
@@ -385,7 +456,7 @@ class CagraWorkload:
     dtype = "f32"
     timing_section = "cagra_search"
 
-    def __init__(self, n=10_000_000, d=96, nq=10_000, k=10, degree=64, itopk=64, seed=1234, rank=0, world=1, walk_bits=16):
+    def __init__(self, n=10_000_000, d=96, nq=10_000, k=10, degree=64, itopk=64, seed=1234, rank=0, world=1, walk_bits=32):
         from cuvs_b200.neighbors import brute_force, cagra
         self.n, self.d, self.nq, self.k, self.degree, self.itopk = n, d, nq, k, degree, itopk
         self.name = f"cagra {n // 1_000_000}M x {d} f32, graph_degree={degree} itopk={itopk} search_width=1, batch {nq}, k={k}"
@@ -406,6 +477,7 @@ class CagraWorkload:
         self.h_neighbors = torch.empty((nq, k), dtype=torch.uint32).pin_memory()
         self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
         self.gt = exact_ground_truth(self.dataset, self.queries, k)
+        self.gt_check = oracle_gt_check(self.dataset, self.queries, k)
         self.recall = None
 
     def step(self, res):
@@ -426,13 +498,13 @@ class CagraWorkload:
     def check(self):
         nb = self.neighbors.to(torch.int64)
         self.recall = (nb.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
-        return self.recall >= 0.95
+        return self.recall >= 0.95 and self.gt_check["ok"]
 
     def config(self):
         return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
                 "graph_degree": self.degree, "itopk": self.itopk,
                 "walk": "fp16 copy of the rows for the walk + fp32 re-rank of the final 32" if self.walk_bits == 16 else "fp32 rows",
-                "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "recall_at_10": self.recall, "ground_truth_check": self.gt_check, "index_build_s": round(self.build_s, 2),
                 "data": "rank-16 gaussian manifold in 96-d + 0.05 noise (embedding-like), seeds 1234/4321",
                 "l2_flush": "256 MiB write between timed steps", "parallelism": "single GPU"}
 
@@ -448,8 +520,8 @@ class CagraWorkload:
                 "hash-deduplicated children are not fetched, so true traffic is lower"}
 
     def cpu_baseline(self, budget_s=20.0):
-        return cpu_exact_knn_rate(self.dataset.cpu().numpy(), self.queries[:1024].cpu().numpy(), self.k, budget_s,
-                                  "the reference has no CPU IVF / graph search; exact kNN is its CPU answer")
+        return cpu_baseline_on_slice(self.dataset, self.queries, self.k, budget_s,
+                                     "the reference has no CPU IVF / graph search; exact kNN is its CPU answer")
 
 
 class IvfFlatWorkload:
@@ -488,6 +560,7 @@ class IvfFlatWorkload:
         self.h_neighbors = torch.empty((nq, k), dtype=torch.int64).pin_memory()
         self.h_distances = torch.empty((nq, k), dtype=torch.float32).pin_memory()
         self.gt = exact_ground_truth(self.dataset, self.queries, k)
+        self.gt_check = oracle_gt_check(self.dataset, self.queries, k) if rank == 0 else None
         self.recall = None
 
     def _search(self, q, res):
@@ -514,11 +587,12 @@ class IvfFlatWorkload:
 
     def check(self):
         self.recall = (self.final_i.unsqueeze(2) == self.gt.unsqueeze(1)).any(dim=2).float().mean().item()
-        return self.recall >= 0.95
+        return self.recall >= 0.95 and (self.gt_check is None or self.gt_check["ok"])
 
     def config(self):
         return {"workload": self.name, "n": self.n, "dim": self.d, "batch": self.nq, "k": self.k, "metric": "sqeuclidean",
-                "n_lists": self.n_lists, "n_probes": self.n_probes, "recall_at_10": self.recall, "index_build_s": round(self.build_s, 2),
+                "n_lists": self.n_lists, "n_probes": self.n_probes, "recall_at_10": self.recall, "ground_truth_check": self.gt_check,
+                "index_build_s": round(self.build_s, 2),
                 "data": "rank-16 gaussian manifold in 128-d + 0.05 noise (embedding-like), seeds 1234/4321",
                 "l2_flush": "256 MiB write between timed steps",
                 "parallelism": "single GPU" if self.world == 1 else
@@ -550,7 +624,15 @@ class IvfFlatWorkload:
         return IvfPqWorkload.cpu_baseline(self, budget_s)
 
 
-WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "cagra": CagraWorkload, "ivf_flat": IvfFlatWorkload}
+class IvfPqC2Workload(IvfPqWorkload):
+    """BASELINE configs[2]: ivf_pq::search 10M x 128 f32, nlist=1024 pq_dim=64 nprobe=64, batch 10k."""
+
+    def __init__(self, n=10_000_000, n_lists=1024, n_probes=64, **kw):
+        super().__init__(n=n, n_lists=n_lists, n_probes=n_probes, **kw)
+
+
+WORKLOADS = {"brute_force": BruteForceWorkload, "ivf_pq": IvfPqWorkload, "ivf_pq_c2": IvfPqC2Workload, "cagra": CagraWorkload,
+             "ivf_flat": IvfFlatWorkload}
 
 
 METRIC_NAME = "QPS @ recall@10>=0.95 (queries/s of one batched 10k-query search() call; recall@10 in config)"
@@ -593,8 +675,10 @@ def run_ours(args):
         kw["n"] = args.n
     if args.nq:
         kw["nq"] = args.nq
-    if args.workload == "ivf_pq":
+    if args.workload in ("ivf_pq", "ivf_pq_c2"):
         kw["lut_dtype"] = args.lut_dtype
+        if args.data_rank:
+            kw["data_rank"] = args.data_rank
         for name in ("n_lists", "n_probes", "refine_ratio", "pq_dim"):
             if getattr(args, name):
                 kw[name] = getattr(args, name)
@@ -694,68 +778,69 @@ def run_ours(args):
             "roofline": wl.roofline(kernel_ms, pk),
         }
         line["roofline"]["traffic"] = ncu_traffic(args.workload, wl)
+        if not ok:
+            line["PARITY_FAILED"] = ("recall@10 below 0.95 or ground-truth machinery disagrees with the oracle — this line is NOT "
+                                     "a valid measurement of the metric")
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = wl.cpu_baseline()
+        if world == 1 and args.workload == "ivf_pq" and not args.no_aux:
+            del wl
+            torch.cuda.empty_cache()
+            line["config"]["harder_data"] = harder_data_point(args, res, timed)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
+def harder_data_point(args, res, timed):
+    """The same search on a HARDER distribution (rank-32 manifold: twice the intrinsic dimension, PQ with 2 dims per code has
+    less to exploit), at 10M rows so that it fits beside the main run: QPS + recall, reported inside the main line's config."""
+    wl = IvfPqWorkload(n=10_000_000, n_lists=4096, n_probes=64, refine_ratio=4, data_rank=32, lut_dtype=args.lut_dtype)
+    for _ in range(3):
+        wl.step(res)
+    res.sync()
+    ms = timed(wl.step, 5)
+    ok = wl.check()
+    return {"workload": wl.name, "data": "rank-32 gaussian manifold + 0.05 noise", "qps": wl.units() * 5 / (ms * 1e-3),
+            "recall_at_10": wl.recall, "ok": bool(ok)}
+
+
 def run_reference(args):
     """Reference arm.  cuVS has no CPU implementation of these searches (only refine_host and hnswlib) and its CUDA build
-    cannot be produced offline, so this times the oracle port — exact fp32 kNN, all host threads — on the
-    SAME data, batch and k as our arm; rank 0 only."""
+    cannot be produced offline, so this times the oracle port — exact fp32 kNN, all host threads, in the
+    pinned-thread subprocess of oracle/cpu_baseline.py — on the SAME tensors as our arm (same torch generator and seeds; on
+    the device when there is one, then copied to the host): a row slice of the dataset (host RAM / time bound), the rate
+    scaled to the full row count.  Each "step" is one timed repeat of the bounded query sample.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     wl = args.workload
-    n = args.n or (10_000_000 if wl in ("ivf_pq", "ivf_flat", "cagra") else 1_000_000)
-    d, nq, k = 128, args.nq or 10_000, 10
-    rng = np.random.default_rng(1234)
-    if wl in ("ivf_pq", "ivf_flat", "cagra"):
-        if wl == "cagra":
-            d = 96
-        A = (np.random.default_rng(99).standard_normal((16, d)) / 4.0).astype(np.float32)
-        ds = np.empty((n, d), np.float32)
-        for s0 in range(0, n, 1 << 20):
-            e = min(n, s0 + (1 << 20))
-            ds[s0:e] = rng.standard_normal((e - s0, 16), dtype=np.float32) @ A + 0.05 * rng.standard_normal((e - s0, d), dtype=np.float32)
-        qs = (rng.standard_normal((1024, 16), dtype=np.float32) @ A + 0.05 * rng.standard_normal((1024, d), dtype=np.float32)).astype(np.float32)
-        name = f"{wl} {n // 1_000_000}M x {d} f32 workload, answered by exact CPU kNN (the reference has no CPU {wl} search)"
-    else:
-        centers = np.random.default_rng(99).standard_normal((max(1, n // 1000), d)).astype(np.float32)
-        ds = (centers[rng.integers(0, len(centers), n)] + 0.25 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
-        qs = (centers[rng.integers(0, len(centers), 1024)] + 0.25 * rng.standard_normal((1024, d), dtype=np.float32)).astype(np.float32)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    d, nq, k = (96 if wl == "cagra" else 128), args.nq or 10_000, 10
+    n = args.n or {"brute_force": 1_000_000, "ivf_pq": 100_000_000}.get(wl, 10_000_000)
+    rows = min(n, CPU_SLICE_ROWS)
+    if wl == "brute_force":
+        g = torch.Generator(device=dev)
+        g.manual_seed(99)
+        centers = torch.randn((max(1, n // 1000), d), generator=g, device=dev)
+        ds = gen_clustered(rows, d, 1234, centers, device=dev)
+        qs = gen_clustered(1024, d, 1234 + 3087, centers, device=dev)
         name = BruteForceWorkload.name
-    threads = os.cpu_count() or 1
-    t0 = time.time()
-    oracle.knn(ds, qs[:4], k)
-    r_scan = 4 / max(time.time() - t0, 1e-9)
-    t0 = time.time()
-    oracle.knn_blocked(ds, qs[:64], k, threads=threads)
-    r_blk = 64 / max(time.time() - t0, 1e-9)
-    use_blk = r_blk > r_scan
-    run = (lambda qq: oracle.knn_blocked(ds, qq, k, threads=threads)) if use_blk else (lambda qq: oracle.knn(ds, qq, k))
-    how = "blocked SGEMM + top-k (oracle.knn_blocked)" if use_blk else "sequential-fmaf scan (oracle.knn, OpenMP)"
-    steps, warm = args.steps, min(args.warmup, 1)
-    m = int(max(8, min(len(qs), 90.0 * max(r_scan, r_blk) / max(steps + warm, 1))))
-    for _ in range(warm):
-        run(qs[:m])
-    t0 = time.time()
-    for _ in range(steps):
-        run(qs[:m])
-    dt = time.time() - t0
-    v = m * steps / dt
+    else:
+        rk = args.data_rank or 16
+        ds = gen_manifold(rows, d, 1234, rank=rk, device=dev)   # == the first `rows` rows of the GPU arm's dataset
+        qs = gen_manifold(1024, d, 1234 + 3087, rank=rk, device=dev)
+        name = f"{wl} {n // 1_000_000}M x {d} f32 workload, answered by exact CPU kNN (the reference has no CPU {wl} search)"
+    budget = max(8.0, 12.0 * max(args.steps, 1) / 3.0)
+    cb = cpu_exact_knn_rate(ds.cpu().numpy(), qs.cpu().numpy(), k, budget, "same tensors as the GPU arm", n_total=n)
+    v = cb["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC_NAME, "value": v, "unit": "queries/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": 3, "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "n": n, "dim": d, "batch": nq, "k": k, "metric": "sqeuclidean", "recall_at_10": 1.0},
-        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{m} queries per step against all {n} rows, exact fp32 kNN, {how}; probe rates scan {r_scan:.1f} q/s, "
-                                   f"blocked {r_blk:.1f} q/s"},
+        "config": {"workload": name, "n": n, "dim": d, "batch": nq, "k": k, "metric": "sqeuclidean", "recall_at_10": 1.0,
+                   "note": "steps/warmup: the CPU arm always runs 1 warm-up + 3 timed repeats of a bounded query sample (median reported)"},
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -776,8 +861,10 @@ def main():
     ap.add_argument("--pq-dim", dest="pq_dim", type=int, default=0)
     ap.add_argument("--lut-dtype", dest="lut_dtype", default="f16", choices=["f32", "f16", "u8"],
                     help="ivf_pq search lut_dtype: f16/u8 (reduced-precision LUT, the usual throughput setting) -> 1-pass bf16 scan; f32 (API default) -> 2-pass scan")
-    ap.add_argument("--walk-bits", dest="walk_bits", type=int, default=16, choices=[16, 32],
+    ap.add_argument("--walk-bits", dest="walk_bits", type=int, default=32, choices=[16, 32],
                     help="cagra: precision of the rows the graph walk reads (16 = fp16 copy + fp32 re-rank, 32 = fp32)")
+    ap.add_argument("--data-rank", dest="data_rank", type=int, default=0, help="intrinsic dimension of the synthetic manifold data (default 16)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the secondary harder-data (rank-32, 10M) measurement of the ivf_pq line")
     ap.add_argument("--itopk", type=int, default=0)
     ap.add_argument("--degree", type=int, default=0)
     args = ap.parse_args()

@@ -197,6 +197,23 @@ inline void dl_expect_matrix(const DLTensor& t, const char* name)
   B2_EXPECTS(t.ndim == 2, "%s must be a 2-D tensor (got ndim=%d)", name, t.ndim);
 }
 
+/** Rows [r0, r0 + rows) of a C-contiguous 2-D tensor as a non-owning view (query batching inside the searches). */
+struct dl_row_slice {
+  DLTensor t;
+  int64_t shape[2];
+  dl_row_slice(const DLTensor& src, int64_t r0, int64_t rows)
+  {
+    t           = src;
+    shape[0]    = rows;
+    shape[1]    = src.shape[1];
+    t.shape     = shape;
+    t.strides   = nullptr;
+    t.data      = static_cast<char*>(src.data) + src.byte_offset + r0 * src.shape[1] * ((src.dtype.bits * src.dtype.lanes + 7) / 8);
+    t.byte_offset = 0;
+  }
+  dl_row_slice(const dl_row_slice&) = delete;
+};
+
 /** Fill a caller-provided DLManagedTensor as a non-owning row-major view (used by index getters). */
 void dl_fill_view(DLManagedTensor* out, void* data, int device, DLDataType dt, int ndim, const int64_t* shape);
 

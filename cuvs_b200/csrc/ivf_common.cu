@@ -60,8 +60,8 @@ __global__ void count_probes_kernel(const uint32_t* __restrict__ probes, int64_t
     atomicAdd(&counts[2 * l + (static_cast<int>(t % n_probes) < near_ranks ? 0 : 1)], 1u);
 }
 
-// single CTA: exclusive scans over lists of (a) pair counts, (b) "has a first item", (c) further items ceil(cnt/128) - 1
-__global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __restrict__ counts, int64_t n_lists,
+// single CTA: exclusive scans over lists of (a) pair counts, (b) "has a first item", (c) further items ceil(cnt/group) - 1
+__global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __restrict__ counts, int64_t n_lists, uint32_t group,
                                                            uint32_t* __restrict__ pair_off, uint32_t* __restrict__ first_off,
                                                            uint32_t* __restrict__ rest_off, int* __restrict__ n_items,
                                                            uint32_t* __restrict__ cursor)
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(1024) scan_lists_kernel(const uint32_t* __rest
     uint32_t c0 = l < n_lists ? counts[2 * l] : 0;
     uint32_t c  = c0 + (l < n_lists ? counts[2 * l + 1] : 0);
     uint32_t f  = c > 0 ? 1u : 0u;
-    uint32_t g  = c > 0 ? (c + 127) / 128 - 1 : 0u;
+    uint32_t g  = c > 0 ? (c + group - 1) / group - 1 : 0u;
     s_pairs[threadIdx.x] = c;
     s_first[threadIdx.x] = f;
     s_rest[threadIdx.x]  = g;
@@ -127,7 +127,7 @@ __global__ void scatter_probes_kernel(const uint32_t* __restrict__ probes, int64
 __global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ pair_off,
                                        const uint32_t* __restrict__ first_off, const uint32_t* __restrict__ rest_off,
                                        const int* __restrict__ n_items, const int64_t* __restrict__ list_offsets,
-                                       int64_t n_lists, int KC, uint32_t max_tiles, tc_item* __restrict__ items)
+                                       int64_t n_lists, int KC, uint32_t max_tiles, uint32_t group, tc_item* __restrict__ items)
 {
   int64_t l = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (l >= n_lists) return;
@@ -136,13 +136,13 @@ __global__ void make_list_items_kernel(const uint32_t* __restrict__ counts, cons
   const uint32_t b_row0  = static_cast<uint32_t>(list_offsets[l]);
   const uint32_t n_tiles = min(max_tiles, static_cast<uint32_t>((list_offsets[l + 1] - list_offsets[l]) / 128));
   const uint32_t n_first = static_cast<uint32_t>(n_items[2]);
-  uint32_t g = (c + 127) / 128;
+  uint32_t g = (c + group - 1) / group;
   for (uint32_t j = 0; j < g; ++j) {
     tc_item it;
-    it.a_row0     = pair_off[2 * l] + j * 128;
+    it.a_row0     = pair_off[2 * l] + j * group;
     it.b_row0     = b_row0;
     it.n_tiles    = n_tiles;
-    it.valid_rows = min(128u, c - j * 128);
+    it.valid_rows = min(group, c - j * group);
     it.out_off    = static_cast<uint64_t>(it.a_row0) * KC;
     items[j == 0 ? first_off[l] : n_first + rest_off[l] + (j - 1)] = it;
   }
@@ -479,13 +479,14 @@ void assign_nearest(resources* res, const __nv_bfloat16* x_hi, const __nv_bfloat
 }
 
 void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_probes, int64_t n_lists,
-                   const int64_t* list_offsets_dev, int KC, probe_buckets& out, int probe_ld, uint32_t max_tiles)
+                   const int64_t* list_offsets_dev, int KC, probe_buckets& out, int probe_ld, uint32_t max_tiles, int group)
 {
+  B2_EXPECTS(group >= 8 && group <= 128, "bucket_probes: group must be within [8, 128]");
   if (probe_ld <= 0) probe_ld = n_probes;
   auto s              = res->stream;
   const int64_t total = nq * n_probes;
   out.n_pairs         = total;
-  out.max_items       = static_cast<int>(total / 128 + n_lists + 1);
+  out.max_items       = static_cast<int>(total / group + n_lists + 1);
   out.slot_of.alloc(static_cast<size_t>(total), s);
   out.pair_query.alloc(static_cast<size_t>(total), s);
   out.pair_list.alloc(static_cast<size_t>(total), s);
@@ -497,13 +498,13 @@ void bucket_probes(resources* res, const uint32_t* probes, int64_t nq, int n_pro
   B2_CUDA(cudaMemsetAsync(counts.data(), 0, sizeof(uint32_t) * 2 * n_lists, s));
   count_launch(4);
   count_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, probe_ld, near_ranks, list_offsets_dev, counts.data());
-  scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, pair_off.data(), first_off.data(), rest_off.data(), out.n_items.data(),
+  scan_lists_kernel<<<1, 1024, 0, s>>>(counts.data(), n_lists, static_cast<uint32_t>(group), pair_off.data(), first_off.data(), rest_off.data(), out.n_items.data(),
                                        cursor.data());
   scatter_probes_kernel<<<blocks_for(total, 256), 256, 0, s>>>(probes, total, n_probes, probe_ld, near_ranks, list_offsets_dev, pair_off.data(),
                                                                 cursor.data(), out.slot_of.data(), out.pair_query.data(),
                                                                 out.pair_list.data());
   make_list_items_kernel<<<blocks_for(n_lists, 128), 128, 0, s>>>(counts.data(), pair_off.data(), first_off.data(), rest_off.data(),
-                                                                   out.n_items.data(), list_offsets_dev, n_lists, KC, max_tiles, out.items.data());
+                                                                   out.n_items.data(), list_offsets_dev, n_lists, KC, max_tiles, static_cast<uint32_t>(group), out.items.data());
   B2_CUDA(cudaGetLastError());
 }
 

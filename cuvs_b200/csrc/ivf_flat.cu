@@ -46,7 +46,7 @@ struct ivf_flat_index {
   tc_rows centers_tc;    // split planes + |c|^2/2 (0 for inner product)
   list_layout lists;
   owned<float> data;         // [rows_total, dim], list-major, zero padding rows
-  owned<int64_t> ids;        // [rows_total], -1 on padding rows
+  owned<int64_t> ids;        // [rows_total], kPadId on padding rows
   owned<float> xn;           // [rows_total] |x|^2 (cosine / certificate use)
   owned<__nv_bfloat16> hi;   // [rows_total, Kp] bf16 rows (normalised for cosine)
   owned<__nv_bfloat16> hx;   // [rows_total, 16] half-norm plane: |x|^2/2, +inf on padding rows (scan_tc.cuh)
@@ -83,7 +83,7 @@ __global__ void half_norms_masked_kernel(const float* __restrict__ xn, const int
 {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
-  hn[i] = ids[i] < 0 ? INFINITY : (zero ? 0.f : 0.5f * xn[i]);
+  hn[i] = ids[i] == kPadId ? INFINITY : (zero ? 0.f : 0.5f * xn[i]);
 }
 
 // same, additionally hiding every row whose source id is not kept by the bitset (bit = 1 keeps): the filtered search
@@ -121,7 +121,7 @@ __global__ void move_rows_kernel(const float* __restrict__ src, const int64_t* _
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= rows * d) return;
   int64_t r = t / d;
-  if (src_ids[r] < 0) return;  // padding row of the old layout
+  if (src_ids[r] == kPadId) return;  // padding row of the old layout
   int c     = static_cast<int>(t % d);
   int64_t o = dst_rows[r];
   dst[o * d + c] = src[t];
@@ -195,7 +195,7 @@ void ivf_flat_extend(resources* res, ivf_flat_index& idx, const float* x, int64_
   owned<int64_t> nids(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)));
   B2_CUDA(cudaMemsetAsync(ndata.data(), 0, sizeof(float) * static_cast<size_t>(nl.rows_total) * idx.dim, s));
   count_launch();
-  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, -1);
+  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, kPadId);
   // 3. move the old rows
   if (idx.lists.rows_total > 0) {
     dbuf<int64_t> dst_old(static_cast<size_t>(idx.lists.rows_total), s);
@@ -294,6 +294,21 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   B2_EXPECTS(n_probes >= 1, "n_probes must be >= 1");
   if (nq == 0) return;
   n_probes         = std::min<uint32_t>(n_probes, idx.n_lists);
+  {
+    // Query batching: the per-(query, probe) workspaces (gathered bf16 query rows, 2 x KC candidate slots, their per-query
+    // concatenation) are bounded to ~3 GiB; slots are uint32, so nq * n_probes also stays below 2^31 per batch.
+    const int64_t per_query = static_cast<int64_t>(n_probes) * (idx.Kp * 2 + 2 * 64 * 8 + 16);
+    int64_t batch = std::max<int64_t>(1, (int64_t(3) << 30) / per_query);
+    batch         = std::min<int64_t>(batch, (int64_t(1) << 31) / std::max<uint32_t>(n_probes, 1));
+    if (nq > batch) {
+      for (int64_t q0 = 0; q0 < nq; q0 += batch) {
+        const int64_t rows = std::min(batch, nq - q0);
+        dl_row_slice qs(qt, q0, rows), ns(nt, q0, rows), ds(dt, q0, rows);
+        ivf_flat_search(res, idx, n_probes, qs.t, ns.t, ds.t, keep_bits, n_bits);
+      }
+      return;
+    }
+  }
   const float* q   = dl_ptr<float>(qt);
   int64_t* out_idx = dl_ptr<int64_t>(nt);
   float* out_dist  = dl_ptr<float>(dt);
@@ -329,7 +344,12 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
   }
 
   // ---- 2. bucket (query, probe) pairs by list
-  const int KC    = k <= 16 ? 16 : 32;
+  // The scan ranks rows by a ONE-pass bf16 score; the exact fp32 re-score below only sees what survives it.  Keep slack
+  // between k and the per-list capacity (and the shared pruning bound, which tracks the KC-th best): a true top-k row whose
+  // bf16 score ranks a few places late must still be a candidate.  k <= 10 -> 16 slots, k <= 32 -> 32 slots; the bound is
+  // only used when KC >= 1.5 k.
+  const int KC    = (k + k / 2 <= 16) ? 16 : 32;
+  const bool use_bound = KC >= k + k / 2;
   const int lists = tc_lists_per_item();
   const int KCW   = KC * lists;
   B2_EXPECTS(KCW >= k, "ivf_flat search: k = %d needs the two-list tensor-core epilogue (CUVS_B200_TC_EPIW=8)", k);
@@ -351,7 +371,7 @@ void ivf_flat_search(resources* res, const ivf_flat_index& idx, uint32_t n_probe
     bnd.idx  = pb.pair_query.data();
     timed_section ts("ivf_flat_scan", s);
     tc_scan_topk(s, res->device, a_hi.data(), nullptr, a_rows, idx.hi.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                 idx.Kp, hx, pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, k <= KC ? &bnd : nullptr);  // the bound tracks a KC-th best: only valid for k <= KC
+                 idx.Kp, hx, pb.items.data(), pb.max_items, pb.n_items.data(), KC, 1, cs.data(), cp.data(), KCW, use_bound ? &bnd : nullptr);
   }
 
   // ---- 4. per query: merge probes by approximate score, exact re-score, ids
@@ -608,7 +628,7 @@ cuvsError_t cuvsIvfFlatDeserialize(cuvsResources_t res, const char* filename, cu
     idx->data.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)) * idx->dim);
     idx->ids.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)));
     B2_CUDA(cudaMemsetAsync(idx->data.data(), 0, sizeof(float) * static_cast<size_t>(R) * idx->dim, r->stream));
-    if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, -1);
+    if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, kPadId);
     std::vector<float> rows;
     std::vector<int64_t> ids;
     for (uint32_t l = 0; l < idx->n_lists; ++l) {

@@ -13,6 +13,9 @@
 
 namespace b200 {
 
+/** id stored on the padding rows of a list (any other int64, negative ones included, is a user id). */
+constexpr int64_t kPadId = INT64_MIN;
+
 struct list_layout {
   int64_t n_lists = 0;
   std::vector<int64_t> h_sizes;    // rows per list

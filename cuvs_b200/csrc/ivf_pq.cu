@@ -27,10 +27,12 @@
 #include "exact.cuh"
 #include "ivf_common.cuh"
 #include "ivf_lists.cuh"
+#include "scan_pq.cuh"
 #include "select_k.cuh"
 #include "timing.hpp"
 
 #include <cuvs/neighbors/ivf_pq.h>
+#include <cuvs_b200/ext.h>
 
 #include <cuda_fp16.h>
 
@@ -63,11 +65,16 @@ struct ivf_pq_index {
   tc_rows centers_tc;
   list_layout lists;
   owned<uint8_t> codes;  // [rows_total, pq_dim], one code per byte
-  owned<int64_t> ids;    // [rows_total], -1 on padding rows
+  owned<int64_t> ids;    // [rows_total], kPadId on padding rows
   // decoded side (path B)
   int Kp = 0;
   owned<__nv_bfloat16> yhat;  // [rows_total, Kp]
   owned<__nv_bfloat16> hx;    // [rows_total, 16] half-norm plane: |y|^2/2 (0 for inner product), +inf on padding rows
+  // streamed side (path C, scan_pq.cu): lane-transposed code tiles + half norms, bank-transposed bf16x2 codebook words.
+  // When the shape is served by the code-streaming kernel the decoded rows above are NOT kept (pq_dim + 4 bytes per
+  // vector instead of 2 * rot_dim + 32).
+  owned<uint8_t> cstream;    // [rows_total / 128, pq_stream_tile_bytes(pq_dim)]
+  owned<uint32_t> cb_words;  // [pq_dim / 32, 256, 32]
   int book() const { return 1 << pq_bits; }
 };
 
@@ -221,7 +228,7 @@ __global__ void pq_decode_kernel(const uint8_t* __restrict__ codes, const int64_
   int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   int lane  = threadIdx.x & 31;
   if (r >= rows) return;
-  const bool pad = ids[r] < 0;
+  const bool pad = ids[r] == kPadId;
   int64_t list   = 0;
   if (per_cluster || ip) {  // binary search of the owning list
     int64_t lo = 0, hi = n_lists;
@@ -254,7 +261,7 @@ __global__ void move_codes_kernel(const uint8_t* __restrict__ src, const int64_t
   int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= rows * pq_dim) return;
   int64_t r = t / pq_dim;
-  if (src_ids[r] < 0) return;
+  if (src_ids[r] == kPadId) return;
   int c     = static_cast<int>(t % pq_dim);
   int64_t o = dst_rows[r];
   dst[o * pq_dim + c] = src[t];
@@ -298,7 +305,7 @@ __global__ void pair_rows_kernel(const float* __restrict__ q_rot, const float* _
                                  const uint32_t* __restrict__ pair_query, const uint32_t* __restrict__ pair_list,
                                  const int* __restrict__ n_live, int64_t rows_total, int rot_dim, int Kp, bool ip,
                                  __nv_bfloat16* __restrict__ a_hi,
-                                 __nv_bfloat16* __restrict__ a_lo, float* __restrict__ add)
+                                 __nv_bfloat16* __restrict__ a_lo, float* __restrict__ add, bool ip_center_in_add)
 {
   int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   int lane  = threadIdx.x & 31;
@@ -313,11 +320,12 @@ __global__ void pair_rows_kernel(const float* __restrict__ q_rot, const float* _
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     a_hi[r * Kp + j] = h;
     if (a_lo) a_lo[r * Kp + j] = __float2bfloat16_rn(v - __bfloat162float(h));
-    nrm = fmaf(v, v, nrm);
+    // L2: |r|^2.  Inner product over code-only rows (the streamed scan decodes y, not c + y): -(q . c) of the pair
+    nrm = (ip && ip_center_in_add) ? ((live && j < rot_dim) ? fmaf(-qr[j], cr[j], nrm) : nrm) : fmaf(v, v, nrm);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-  if (lane == 0 && live) add[r] = ip ? 0.f : nrm;
+  if (lane == 0 && live) add[r] = (ip && !ip_center_in_add) ? 0.f : nrm;
 }
 
 // out[q, p*KCW + c] = add[slot] + scale * s   (per-query concatenation of its probes' candidates)
@@ -468,8 +476,9 @@ pq_lut_scan_kernel(const float* __restrict__ q_rot, const float* __restrict__ ce
         if (at < kLutBuf) { bv[at] = fs; bp[at] = static_cast<uint32_t>(row0 + i); }
       }
     }
-    __syncthreads();
-    if (s_cnt > kLutBuf - static_cast<int>(blockDim.x)) compact(KC);
+    // one snapshot of s_cnt decides for the whole CTA (compact() has barriers inside): every thread votes AFTER all pushes
+    // of this round and BEFORE anyone can push again
+    if (__syncthreads_or(s_cnt > kLutBuf - static_cast<int>(blockDim.x))) compact(KC);
   }
   compact(KC);
   const int kept = s_cnt;
@@ -548,7 +557,20 @@ void refresh_decoded(resources* res, ivf_pq_index& idx)
   auto s          = res->stream;
   const int64_t R = idx.lists.rows_total;
   idx.Kp          = tc_pad_k(idx.rot_dim);
+  idx.cstream.release();
+  idx.cb_words.release();
   if (idx.conservative || !tc_supported(res->device, idx.rot_dim)) { idx.yhat.release(); idx.hx.release(); return; }
+  static const bool keep_decoded = getenv("CUVS_B200_PQ_KEEP_DECODED") != nullptr;  // A/B experiments against path (B)
+  if (!keep_decoded && idx.Kp == idx.rot_dim &&
+      pq_stream_supported(res->device, idx.pq_dim, idx.pq_len, idx.pq_bits, idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_SUBSPACE)) {
+    idx.yhat.release();
+    idx.hx.release();
+    idx.cstream.alloc(static_cast<size_t>(std::max<int64_t>(R / 128, 1)) * pq_stream_tile_bytes(idx.pq_dim));
+    idx.cb_words.alloc(static_cast<size_t>(idx.pq_dim / 32) * 256 * 32);
+    pq_stream_build(s, idx.codes.data(), idx.ids.data(), kPadId, R, idx.pq_dim, idx.pq_centers.data(), is_ip(idx.metric),
+                    idx.cstream.data(), idx.cb_words.data());
+    return;
+  }
   idx.yhat.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * idx.Kp);
   idx.hx.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * 16);
   if (R == 0) return;
@@ -637,7 +659,7 @@ void ivf_pq_extend(resources* res, ivf_pq_index& idx, const DLTensor& t, const i
   owned<int64_t> nids(static_cast<size_t>(std::max<int64_t>(nl.rows_total, 1)));
   B2_CUDA(cudaMemsetAsync(ncodes.data(), 0, static_cast<size_t>(nl.rows_total) * idx.pq_dim, s));
   count_launch();
-  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, -1);
+  fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, kPadId);
   if (idx.lists.rows_total > 0) {
     dbuf<int64_t> dst_old(static_cast<size_t>(idx.lists.rows_total), s);
     count_launch(2);
@@ -689,6 +711,7 @@ void init_shape(ivf_pq_index& idx, const cuvsIvfPqIndexParams& p, int dim)
   idx.conservative  = p.conservative_memory_allocation;
   idx.kmeans_n_iters = p.kmeans_n_iters;
   B2_EXPECTS(idx.pq_bits >= 4 && idx.pq_bits <= 8, "pq_bits must be within [4, 8]");
+  B2_EXPECTS(idx.pq_len >= 1 && idx.pq_len <= 32, "pq_len = ceil(dim / pq_dim) = %d is outside [1, 32] (dim %d, pq_dim %d)", idx.pq_len, dim, idx.pq_dim);
   B2_EXPECTS(is_l2(p.metric) || p.metric == InnerProduct || p.metric == CosineExpanded, "ivf_pq: unsupported metric %d", int(p.metric));
   B2_EXPECTS(p.metric != CosineExpanded, "ivf_pq: cosine metric is not supported by this build yet");
 }
@@ -775,6 +798,23 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   B2_EXPECTS(sp.internal_distance_dtype == CUDA_R_32F || sp.internal_distance_dtype == CUDA_R_16F, "unsupported internal_distance_dtype");
   if (nq == 0) return;
   const uint32_t n_probes = std::min<uint32_t>(sp.n_probes, idx.n_lists);
+  {
+    // Query batching (ivf_pq_search.cuh:960-1010 loops over max_internal_batch_size): the per-(query, probe) workspaces
+    // below — residual rows (Kp bf16 per pass) and 2 x KC candidate slots — are bounded to ~3 GiB; a 10k x 48-probe batch
+    // needs 0.3 GiB and runs in one piece.  Slots are uint32: nq * n_probes must stay below 2^32 as well.
+    const int64_t per_query = static_cast<int64_t>(n_probes) * (2 * idx.Kp * 2 + 64 * 8 + 16);
+    int64_t batch = std::max<int64_t>(1, (int64_t(3) << 30) / per_query);
+    batch         = std::min<int64_t>(batch, (int64_t(1) << 31) / std::max<uint32_t>(n_probes, 1));
+    if (sp.max_internal_batch_size > 0 && n_probes > 256) batch = std::min<int64_t>(batch, std::max<uint32_t>(sp.max_internal_batch_size, 128));
+    if (nq > batch) {
+      for (int64_t q0 = 0; q0 < nq; q0 += batch) {
+        const int64_t rows = std::min(batch, nq - q0);
+        dl_row_slice qs(qt, q0, rows), ns(nt, q0, rows), ds(dt, q0, rows);
+        ivf_pq_search(res, idx, sp, qs.t, ns.t, ds.t);
+      }
+      return;
+    }
+  }
   const float* q   = dl_ptr<float>(qt);
   int64_t* out_idx = dl_ptr<int64_t>(nt);
   float* out_dist  = dl_ptr<float>(dt);
@@ -795,17 +835,21 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   // residual rounded to bf16: the same class of approximation, at tensor-core speed.  CUVS_B200_PQ_PATH=lut forces the
   // faithful LUT kernel (bit-level emulation of the fp16 / fp_8bit<5> LUT entries).
   const bool reduced = !(sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F);
-  const bool use_tc  = env_path() == 1 ? false : idx.yhat.data() != nullptr;
+  const bool use_stream = env_path() != 1 && idx.cstream.data() != nullptr && k <= 32;  // (C) codes streamed + decoded on the SM
+  const bool use_tc     = use_stream || (env_path() == 1 ? false : idx.yhat.data() != nullptr);
   const int passes   = reduced ? 1 : 2;
-  const int lists = use_tc ? tc_lists_per_item() : 1;
+  const int lists = use_stream ? 1 : (use_tc ? tc_lists_per_item() : 1);
   // candidates kept per (query, probe): the tensor-core epilogue keeps `lists` sorted lists of KC (one per column half of
   // the tile); for k > KC the union of the two half lists stands in for the pair's top-k (exact whenever no more than KC of
   // them fall into one half — an approximation only the k > 32 candidate-generation use case can see)
   const int KC    = k <= 16 ? 16 : (k <= 32 || use_tc ? 32 : 64);
   const int KCW   = KC * lists;
-  B2_EXPECTS(KCW >= k, "ivf_pq search: k = %d needs the two-list tensor-core epilogue (CUVS_B200_TC_EPIW=8) or the LUT path", k);
+  B2_EXPECTS(KCW >= k, "ivf_pq search: k = %d > 32 needs an index with decoded rows (CUVS_B200_PQ_KEEP_DECODED=1) or the LUT path (CUVS_B200_PQ_PATH=lut)", k);
+  // queries per work item: 128 for the query-major kernels; the streamed kernel takes the list rows as the MMA's M side
+  // and 32 / 64 / 128 probing queries as N (picked from the average number of pairs per list)
+  const int group = use_stream ? pq_stream_group(static_cast<double>(nq) * n_probes / std::max<uint32_t>(idx.n_lists, 1), KC, passes) : 128;
   probe_buckets pb;
-  bucket_probes(res, probes.data(), nq, static_cast<int>(n_probes), idx.n_lists, idx.lists.d_offsets.data(), KCW, pb);
+  bucket_probes(res, probes.data(), nq, static_cast<int>(n_probes), idx.n_lists, idx.lists.d_offsets.data(), KCW, pb, 0, 0xffffffffu, group);
   dbuf<float> cs(static_cast<size_t>(pb.n_pairs) * KCW, s);
   dbuf<uint32_t> cp(static_cast<size_t>(pb.n_pairs) * KCW, s);
   dbuf<float> add;
@@ -821,7 +865,7 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
     count_launch();
     pair_rows_kernel<<<blocks_for(a_rows * 32, 256), 256, 0, s>>>(q_rot.data(), idx.centers_rot.data(), pb.pair_query.data(),
                                                                    pb.pair_list.data(), pb.n_items.data() + 1, a_rows, idx.rot_dim, idx.Kp, ip,
-                                                                   a_hi.data(), a_lo.data(), add.data());
+                                                                   a_hi.data(), a_lo.data(), add.data(), use_stream);
     B2_CUDA(cudaGetLastError());
     scale = ip ? 1.0f : 2.0f;  // L2: |r|^2 + 2 (|y|^2/2 - r.y); IP: -(q.(c+y))
     {
@@ -837,8 +881,13 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
       bnd.scale = scale;
       bnd.kth   = k;  // only the query's k best survive the merge below
       timed_section ts("pq_scan", s);
-      tc_scan_topk(s, res->device, a_hi.data(), a_lo.data(), a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
-                   idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, passes, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
+      if (use_stream)
+        pq_stream_scan(s, res->device, a_hi.data(), a_lo.data(), a_rows, idx.Kp, idx.cstream.data(), idx.cb_words.data(), idx.pq_dim,
+                       pb.items.data(), pb.max_items, pb.n_items.data(), group, KC, passes, cs.data(), cp.data(), KCW,
+                       bkeys.data() ? &bnd : nullptr);
+      else
+        tc_scan_topk(s, res->device, a_hi.data(), a_lo.data(), a_rows, idx.yhat.data(), nullptr, std::max<int64_t>(idx.lists.rows_total, 128),
+                     idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, passes, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
     }
   } else {
     const int book      = idx.book();
@@ -935,6 +984,19 @@ cuvsError_t cuvsIvfPqIndexDestroy(cuvsIvfPqIndex_t index)
     if (!index) return;
     delete reinterpret_cast<ivf_pq_index*>(index->addr);
     delete index;
+  });
+}
+
+cuvsError_t cuvsB200IvfPqIndexInfo(cuvsIvfPqIndex_t index, int* path, int64_t* device_bytes)
+{
+  return guarded([=] {
+    const ivf_pq_index& idx = pq_of(index);
+    if (path) *path = idx.cstream.data() ? 2 : (idx.yhat.data() ? 1 : 0);
+    if (device_bytes)
+      *device_bytes = static_cast<int64_t>(idx.codes.size() + idx.ids.size() * 8 + idx.cstream.size() + idx.cb_words.size() * 4 +
+                                           idx.yhat.size() * 2 + idx.hx.size() * 2 + idx.centers.size() * 4 + idx.centers_ext.size() * 4 +
+                                           idx.centers_rot.size() * 4 + idx.rotation.size() * 4 + idx.pq_centers.size() * 4 +
+                                           (idx.centers_tc.hi.size() + idx.centers_tc.lo.size() + idx.centers_tc.hx.size()) * 2);
   });
 }
 
@@ -1241,7 +1303,7 @@ cuvsError_t cuvsIvfPqDeserialize(cuvsResources_t res, const char* filename, cuvs
     idx->codes.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)) * idx->pq_dim);
     idx->ids.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)));
     B2_CUDA(cudaMemsetAsync(idx->codes.data(), 0, static_cast<size_t>(R) * idx->pq_dim, r->stream));
-    if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, -1);
+    if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, kPadId);
     std::vector<uint8_t> codes;
     std::vector<int64_t> ids;
     for (uint32_t l = 0; l < idx->n_lists; ++l) {

@@ -1,0 +1,682 @@
+// IVF-PQ fine scan for sm_100a: PQ codes streamed from HBM, decoded on the SM, contracted on tcgen05, top-k' filtered
+// against per-query thresholds.
+//
+// Replaces   cpp/src/neighbors/ivf_pq/detail/jit_lto_kernels/compute_similarity_impl.cuh:77-173
+//            (+ create_lut_impl.cuh:16-79, compute_score_impl.cuh:53-79, compute_distances_impl.cuh:58-100)
+// Reference formulation: one CTA per (query, probe); LUT[pq_dim][256] in shared memory; every (query, row, subspace)
+// costs one shared-memory gather; the list's codes are re-read from L2/HBM by every probing query.
+// Here: work item = (list, <= NQ probing queries).  Per 128-row tile of the list
+//
+//   warp 0      producer   one cp.async.bulk of the tile's block of the code stream (128 * pq_dim code bytes in "lane-
+//                          transposed" order + 128 half-norms = 8.7 KB at pq_dim 64) into a 2..7-deep mbarrier ring;
+//                          per item one TMA box with the NQ residual rows (bf16, SWIZZLE_128B)
+//   warps 2-9   decode     lane l owns subspaces l and l+32: its 16 code bytes per 16 rows arrive with one 128-bit
+//                          shared load; codebook words sit at [half][code][lane] (bank == lane), so a row's 64 entries are
+//                          fetched with two conflict-free LDS.32 per lane and written with two STS.32 into the 128-byte-
+//                          swizzled K-major operand tile (bf16 row = 256 B).  4.5 shared-memory wavefronts per row.
+//   warp 1      MMA        D[128 rows x NQ queries] (+)= Y_tile . R^T : tcgen05.mma kind::f16, M = 128 (rows), N = NQ, 8 K-steps
+//                          + 1 step that adds -|y|^2/2 (three bf16 pieces x ones); accumulators in a 4-deep TMEM ring
+//   warps 10-13 epilogue   thread = row, columns = queries: tcgen05.ld 32 columns, compare against the queries' running
+//                          thresholds (shared memory), push the rare hits into per-query candidate buffers; a buffer that
+//                          overflows is compacted to its KC best by one warp (redux-based selection) and the threshold
+//                          tightened; one named barrier per tile.
+//
+// With few probing queries per list (100M rows / 16k lists / 10k-query batches: ~30) the accumulator is 128 x 32..64
+// instead of the 128 x 128 of the query-major kernel (scan_tc.cu), the rows fill the MMA's M side completely, and HBM
+// traffic per row is pq_dim + 4 bytes instead of a 2 * rot_dim + 32 byte decoded row.
+#include "common.hpp"
+#include "ptx_sm100.cuh"
+#include "scan_pq.cuh"
+#include "timing.hpp"
+
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+
+namespace b200 {
+namespace {
+
+constexpr int kDecWarps   = 8;
+constexpr int kEpiWarps   = 4;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads    = 64 + 32 * kDecWarps + kEpiThreads;  // 448
+constexpr int kEpiWarp0   = 2 + kDecWarps;                      // first epilogue warp (10: warp & 3 covers all TMEM quarters)
+constexpr int kDecStages  = 2;
+constexpr int kAcc        = 4;   // TMEM accumulator ring
+constexpr int kSched      = 4;   // work-item ring
+constexpr int kMaxCStages = 8;
+constexpr int kDecTile    = 128 * 128;  // one k-block of the decoded tile: 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int kExtTile    = 128 * 32;   // half-norm K extension: 128 rows x 16 bf16
+constexpr int kSmemLimit  = 227 * 1024;
+
+struct pq_args {
+  const uint8_t* stream;
+  const uint32_t* cb_words;
+  const tc_item* items;
+  const int* n_items_dev;
+  int* sched;
+  float* out_score;
+  uint32_t* out_pos;
+  int64_t out_row_stride;
+  int* b_keys;
+  const uint32_t* b_idx;
+  const float* b_add;
+  float b_scale;
+  int kth;
+  int n_items_host;
+  int KC;
+  int cap;      // candidate buffer entries per query (KC < cap <= 64)
+  int cstages;  // code ring depth
+  int blk;      // bytes of one tile block of the stream
+};
+
+__device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred)
+{
+  uint32_t r;
+  asm volatile(
+    "{\n\t"
+    ".reg .pred pi, po;\n\t"
+    "setp.ne.u32 pi, %1, 0;\n\t"
+    "bar.red.or.pred po, %2, %3, pi;\n\t"
+    "selp.u32 %0, 1, 0, po;\n\t"
+    "}\n"
+    : "=r"(r)
+    : "r"(static_cast<uint32_t>(pred)), "r"(id), "r"(nthreads)
+    : "memory");
+  return r != 0;
+}
+
+// monotone float -> uint32 (bigger float = bigger key); never 0 for a real float
+__device__ __forceinline__ uint32_t okey(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
+__device__ __forceinline__ uint32_t okey_inv(uint32_t k) { return (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; }
+
+template <int NQ, int NKB, int PASSES>
+struct layout {
+  static constexpr int q_tile     = NQ * 128;                       // one k-block of the residual rows
+  static constexpr int q_bytes    = PASSES * NKB * q_tile;
+  static constexpr int dec_stage  = NKB * kDecTile + kExtTile;
+  static constexpr int ones_bytes = NQ * 32;
+  static constexpr int cb_bytes   = NKB * 32768;
+  static constexpr int off_q      = 0;
+  static constexpr int off_dec    = off_q + q_bytes;
+  static constexpr int off_ones   = off_dec + kDecStages * dec_stage;
+  static constexpr int off_cb     = off_ones + ones_bytes;
+  static constexpr int off_thr    = off_cb + cb_bytes;
+  static constexpr int off_cnt    = off_thr + NQ * 4;
+  static constexpr int off_bars   = off_cnt + NQ * 4;
+  static constexpr int n_bars     = 2 * kMaxCStages + 2 * kDecStages + 2 + 2 * kAcc + 2 * kSched;
+  static constexpr int off_item   = off_bars + n_bars * 8;
+  static constexpr int off_tmem   = off_item + kSched * 4;
+  static constexpr int off_cand   = (off_tmem + 4 + 15) / 16 * 16;   // [NQ][cap] uint2, then the code ring
+  static constexpr int tmem_cols  = kAcc * NQ;
+  static_assert(q_tile % 1024 == 0 && dec_stage % 1024 == 0, "operand tiles need 1024-byte alignment");
+};
+
+template <int NQ, int NKB, int PASSES>
+__global__ void __launch_bounds__(kThreads, 1)
+pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo, const pq_args P)
+{
+  using L = layout<NQ, NKB, PASSES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (threadIdx.x == 0 && (ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* sQ     = smem_raw + L::off_q;
+  uint8_t* sDec   = smem_raw + L::off_dec;
+  uint8_t* sOnes  = smem_raw + L::off_ones;
+  uint32_t* sCb   = reinterpret_cast<uint32_t*>(smem_raw + L::off_cb);
+  float* sThr     = reinterpret_cast<float*>(smem_raw + L::off_thr);
+  int* sCnt       = reinterpret_cast<int*>(smem_raw + L::off_cnt);
+  uint64_t* bars  = reinterpret_cast<uint64_t*>(smem_raw + L::off_bars);
+  uint64_t* c_full  = bars;
+  uint64_t* c_empty = c_full + kMaxCStages;
+  uint64_t* d_full  = c_empty + kMaxCStages;
+  uint64_t* d_empty = d_full + kDecStages;
+  uint64_t* q_full  = d_empty + kDecStages;
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* t_full  = q_empty + 1;
+  uint64_t* t_empty = t_full + kAcc;
+  uint64_t* s_full  = t_empty + kAcc;
+  uint64_t* s_empty = s_full + kSched;
+  int* s_item       = reinterpret_cast<int*>(smem_raw + L::off_item);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L::off_tmem);
+  uint2* sCand    = reinterpret_cast<uint2*>(smem_raw + L::off_cand);
+  uint8_t* sCode  = smem_raw + L::off_cand + NQ * P.cap * 8;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int n_items = P.n_items_dev ? *P.n_items_dev : P.n_items_host;
+  const uint32_t ncs = static_cast<uint32_t>(P.cstages);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ_hi);
+    if (PASSES == 2) ptx::prefetch_tmap(&tmQ_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxCStages; ++s) {
+      ptx::mbar_init(&c_full[s], 1);
+      ptx::mbar_init(&c_empty[s], kDecWarps);
+    }
+    for (int s = 0; s < kDecStages; ++s) {
+      ptx::mbar_init(&d_full[s], kDecWarps);
+      ptx::mbar_init(&d_empty[s], 1);
+    }
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(q_empty, 1);
+    for (int s = 0; s < kAcc; ++s) {
+      ptx::mbar_init(&t_full[s], 1);
+      ptx::mbar_init(&t_empty[s], kEpiWarps);
+    }
+    for (int s = 0; s < kSched; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&s_empty[s], 1 + kDecWarps + kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  // codebook words -> shared memory ([half][code][lane]); the constant "ones" operand of the half-norm step: every row
+  // {1, 1, 1, 0, 0, 0, 0, 0} in BOTH 16-byte chunks (identical chunks: invariant under the 32-byte swizzle)
+  for (int i = threadIdx.x; i < L::cb_bytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(sCb)[i] = reinterpret_cast<const uint4*>(P.cb_words)[i];
+  for (int i = threadIdx.x; i < L::ones_bytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);
+  ptx::fence_proxy_async();
+  if (warp == 2) { ptx::tmem_alloc<L::tmem_cols>(tmem_slot); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer (whole warp loops, one elected lane issues)
+    uint32_t cs = 0, cph = 0, qph = 0, ss = 0, sp = 0;
+    for (;;) {
+      ptx::mbar_wait(&s_empty[ss], sp ^ 1);
+      int it = 0;
+      if (lane == 0) {
+        it = atomicAdd(P.sched, 1);
+        if (it >= n_items) it = -1;
+        s_item[ss] = it;
+        ptx::mbar_arrive(&s_full[ss]);
+      }
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      tc_item item = P.items[it];
+      item.a_row0  = __shfl_sync(0xffffffffu, item.a_row0, 0);
+      item.b_row0  = __shfl_sync(0xffffffffu, item.b_row0, 0);
+      item.n_tiles = __shfl_sync(0xffffffffu, item.n_tiles, 0);
+      ptx::mbar_wait(q_empty, qph ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(q_full, L::q_bytes);
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          ptx::tma_load_2d(sQ + kb * L::q_tile, &tmQ_hi, q_full, kb * 64, static_cast<int32_t>(item.a_row0));
+          if (PASSES == 2) ptx::tma_load_2d(sQ + (NKB + kb) * L::q_tile, &tmQ_lo, q_full, kb * 64, static_cast<int32_t>(item.a_row0));
+        }
+      }
+      qph ^= 1;
+      const uint8_t* src = P.stream + static_cast<int64_t>(item.b_row0 >> 7) * P.blk;
+      for (uint32_t t = 0; t < item.n_tiles; ++t) {
+        ptx::mbar_wait(&c_empty[cs], cph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&c_full[cs], static_cast<uint32_t>(P.blk));
+          ptx::bulk_load_1d(sCode + cs * P.blk, src + static_cast<int64_t>(t) * P.blk, static_cast<uint32_t>(P.blk), &c_full[cs]);
+        }
+        if (++cs == ncs) { cs = 0; cph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NQ);
+    const uint32_t q_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sQ));
+    const uint32_t d_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sDec));
+    const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_u32(sOnes));
+    uint32_t ds = 0, dph = 0, acc = 0, aph = 0, qph = 0, ss = 0, sp = 0;
+    for (;;) {
+      ptx::mbar_wait(&s_full[ss], sp);
+      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);
+      if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      const uint32_t n_tiles = __shfl_sync(0xffffffffu, P.items[it].n_tiles, 0);
+      ptx::mbar_wait(q_full, qph);
+      ptx::tc_fence_after_sync();
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        ptx::mbar_wait(&t_empty[acc], aph ^ 1);
+        ptx::mbar_wait(&d_full[ds], dph);
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+          const uint32_t d_tmem = tmem_base + acc * NQ;
+          const uint32_t a0     = d_lo0 + ds * (L::dec_stage >> 4);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = a0 + kb * (kDecTile >> 4) + k * 2;  // decoded rows: the M side
+              const uint32_t b = q_lo0 + kb * (L::q_tile >> 4) + k * 2;
+              ptx::mma_bf16_ss_lohi(d_tmem, a, ptx::kDescHiSw128, b, ptx::kDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (PASSES == 2)
+                ptx::mma_bf16_ss_lohi(d_tmem, a, ptx::kDescHiSw128, b + NKB * (L::q_tile >> 4), ptx::kDescHiSw128, idesc, 1u);
+            }
+          }
+          // -= |y|^2/2 : ext rows hold the three bf16 pieces of -hn/2 in both chunks, ones rows three 1s in both chunks
+          ptx::mma_bf16_ss_lohi(d_tmem, a0 + NKB * (kDecTile >> 4), ptx::kDescHiSw32, ones_lo, ptx::kDescHiSw32, idesc, 1u);
+          ptx::mma_commit(&d_empty[ds]);
+          ptx::mma_commit(&t_full[acc]);
+        }
+        if (++ds == kDecStages) { ds = 0; dph ^= 1; }
+        if (++acc == kAcc) { acc = 0; aph ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::mma_commit(q_empty);
+      qph ^= 1;
+    }
+  } else if (warp < kEpiWarp0) {
+    // ------------------------------------------------------------------ decode warps: 16 rows of every tile each
+    const int dw = warp - 2;
+    uint32_t offx[8];  // byte offset of this lane's word inside row x of an 8-row swizzle atom
+#pragma unroll
+    for (int x = 0; x < 8; ++x) offx[x] = x * 128 + ((((lane >> 2) ^ x) & 7) << 4) + ((lane & 3) << 2);
+    const uint8_t* cb_lane = reinterpret_cast<const uint8_t*>(sCb) + lane * 4;
+    uint32_t cs = 0, cph = 0, ds = 0, dph = 0, ss = 0, sp = 0;
+    for (;;) {
+      ptx::mbar_wait(&s_full[ss], sp);
+      const int it = s_item[ss];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      const uint32_t n_tiles = P.items[it].n_tiles;
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        ptx::mbar_wait(&c_full[cs], cph);
+        const uint8_t* cst = sCode + cs * P.blk;
+        uint4 cw[NKB];
+#pragma unroll
+        for (int h = 0; h < NKB; ++h) cw[h] = *reinterpret_cast<const uint4*>(cst + dw * (NKB * 512) + h * 512 + lane * 16);
+        const float hn = reinterpret_cast<const float*>(cst + NKB * 4096)[16 * dw + (lane & 15)];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);  // the codes are in registers: hand the ring slot back
+        if (++cs == ncs) { cs = 0; cph ^= 1; }
+
+        ptx::mbar_wait(&d_empty[ds], dph ^ 1);
+        uint8_t* dst = sDec + ds * L::dec_stage + (2 * dw) * 1024;
+#pragma unroll
+        for (int h = 0; h < NKB; ++h) {
+          const uint32_t w4[4] = {cw[h].x, cw[h].y, cw[h].z, cw[h].w};
+          uint32_t val[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t c = (w4[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+            val[i] = *reinterpret_cast<const uint32_t*>(cb_lane + h * 32768 + c * 128);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            *reinterpret_cast<uint32_t*>(dst + h * kDecTile + (i >> 3) * 1024 + offx[i & 7]) = val[i];
+        }
+        if (lane < 16) {
+          // -hn/2 as three bf16 pieces (exact), identical in both 16-byte chunks of the row; +inf (padding) -> -inf
+          const float hh = -0.5f * hn;
+          __nv_bfloat16 p0 = __float2bfloat16_rn(hh), p1 = __float2bfloat16_rn(0.f), p2 = p1;
+          if (!isinf(hh)) {
+            const float r1 = hh - __bfloat162float(p0);
+            p1             = __float2bfloat16_rn(r1);
+            p2             = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+          }
+          const uint32_t w0 = static_cast<uint32_t>(__bfloat16_as_ushort(p0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(p1)) << 16);
+          const uint32_t w1 = static_cast<uint32_t>(__bfloat16_as_ushort(p2));
+          uint4* ext = reinterpret_cast<uint4*>(sDec + ds * L::dec_stage + NKB * kDecTile + (16 * dw + lane) * 32);
+          ext[0] = make_uint4(w0, w1, 0u, 0u);
+          ext[1] = make_uint4(w0, w1, 0u, 0u);
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&d_full[ds]);
+        if (++ds == kDecStages) { ds = 0; dph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: thread = list row, columns = queries
+    const int ew      = warp - kEpiWarp0;
+    const int quarter = warp & 3;
+    const int row     = quarter * 32 + lane;
+    const int te      = static_cast<int>(threadIdx.x) - 32 * kEpiWarp0;  // 0..127
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int cap = P.cap, KC = P.KC;
+    const int kth = (P.kth > 0 && P.kth < KC) ? P.kth : KC;
+    constexpr int NCH = NQ / 32;
+    uint32_t acc = 0, aph = 0, ss = 0, sp = 0;
+
+    // compaction of column `col` by one warp: the KC best of its buffer, lane j ends up with the j-th best
+    // (key = order(t) << 32 | ~pos, 0 = none); returns the number kept
+    auto select_best = [&](int col, unsigned long long& mine) -> int {
+      const int n = min(sCnt[col], cap);
+      unsigned long long k0 = 0, k1 = 0;
+      if (lane < n) { const uint2 e = sCand[col * cap + lane]; k0 = (static_cast<unsigned long long>(okey(e.x)) << 32) | (~e.y); }
+      if (lane + 32 < n) { const uint2 e = sCand[col * cap + lane + 32]; k1 = (static_cast<unsigned long long>(okey(e.x)) << 32) | (~e.y); }
+      mine   = 0;
+      int nk = 0;
+      for (int j = 0; j < KC; ++j) {
+        const unsigned long long m = k0 > k1 ? k0 : k1;
+        const uint32_t mh = static_cast<uint32_t>(m >> 32);
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, mh);
+        if (hi == 0) break;
+        const uint32_t lo = __reduce_max_sync(0xffffffffu, mh == hi ? static_cast<uint32_t>(m) : 0u);
+        const unsigned long long best = (static_cast<unsigned long long>(hi) << 32) | lo;
+        if (k0 == best) k0 = 0;
+        else if (k1 == best) k1 = 0;
+        if (lane == j) mine = best;
+        nk = j + 1;
+      }
+      return nk;
+    };
+    auto compact = [&](int col) {
+      unsigned long long mine;
+      const int nk = select_best(col, mine);
+      __syncwarp();
+      if (lane < nk) sCand[col * cap + lane] = make_uint2(okey_inv(static_cast<uint32_t>(mine >> 32)), ~static_cast<uint32_t>(mine));
+      const uint32_t kbits = __shfl_sync(0xffffffffu, okey_inv(static_cast<uint32_t>(mine >> 32)), kth - 1);
+      if (lane == 0) {
+        sCnt[col] = nk;
+        if (nk >= kth) sThr[col] = fmaxf(sThr[col], __uint_as_float(kbits));
+      }
+      __syncwarp();
+    };
+
+    for (;;) {
+      ptx::mbar_wait(&s_full[ss], sp);
+      const int it = s_item[ss];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
+      if (++ss == kSched) { ss = 0; sp ^= 1; }
+      if (it < 0) break;
+      const tc_item item = P.items[it];
+      // per-column state: running threshold in t = -(score) units (a row is a candidate iff t > thr), empty buffer
+      for (int col = te; col < NQ; col += kEpiThreads) {
+        float thr = INFINITY;  // columns past the item's queries never collect anything
+        if (static_cast<uint32_t>(col) < item.valid_rows) {
+          thr = -INFINITY;
+          if (P.b_keys != nullptr) {
+            const uint32_t arow = item.a_row0 + col;
+            const int kb        = *reinterpret_cast<volatile int*>(P.b_keys + (P.b_idx ? P.b_idx[arow] : arow));
+            const float bv      = __int_as_float(kb >= 0 ? kb : kb ^ 0x7fffffff);
+            thr                 = -((bv - (P.b_add ? P.b_add[arow] : 0.f)) / P.b_scale);
+          }
+        }
+        sThr[col] = thr;
+        sCnt[col] = 0;
+      }
+      ptx::named_bar_sync(1, kEpiThreads);
+
+      for (uint32_t t = 0; t < item.n_tiles; ++t) {
+        ptx::mbar_wait(&t_full[acc], aph);
+        ptx::tc_fence_after_sync();
+        const uint32_t pos   = item.b_row0 + t * 128 + row;
+        const uint32_t taddr = t_lane + acc * NQ;
+        uint32_t pend[NCH];
+        // one chunk of 32 query columns: returns the columns whose candidate could not be stored (buffer full)
+        auto do_chunk = [&](int c, uint32_t only) -> uint32_t {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+          const float4* th4 = reinterpret_cast<const float4*>(sThr + c * 32);
+          float th[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x = th4[j4];
+            th[4 * j4] = x.x; th[4 * j4 + 1] = x.y; th[4 * j4 + 2] = x.z; th[4 * j4 + 3] = x.w;
+          }
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]) - th[j]);
+          uint32_t left = 0;
+          if (m > 0.f) {
+            uint32_t hit = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(v[j]) > th[j]) ? (1u << j) : 0u;
+            hit &= only;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (hit & (1u << j)) {
+                const int col = c * 32 + j;
+                const int at  = atomicAdd(&sCnt[col], 1);
+                if (at < cap) sCand[col * cap + at] = make_uint2(v[j], pos);
+                else left |= 1u << j;
+              }
+            }
+          }
+          return left;
+        };
+        bool any_left = false;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          pend[c] = do_chunk(c, 0xffffffffu);
+          any_left |= pend[c] != 0;
+        }
+        __syncwarp();
+        while (bar_red_or(1, kEpiThreads, any_left)) {
+          for (int col = ew; col < NQ; col += kEpiWarps)
+            if (sCnt[col] > cap) compact(col);  // (warp-uniform: every lane reads the same counter)
+          ptx::named_bar_sync(1, kEpiThreads);
+          any_left = false;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (pend[c]) pend[c] = do_chunk(c, pend[c]);  // re-read from TMEM, re-test against the tightened thresholds
+            any_left |= pend[c] != 0;
+          }
+          __syncwarp();
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+        if (++acc == kAcc) { acc = 0; aph ^= 1; }
+      }
+
+      // item done: every column's KC best -> global; publish the query's k-th best for the other items of the same query
+      for (int col = ew; col < static_cast<int>(min(item.valid_rows, static_cast<uint32_t>(NQ))); col += kEpiWarps) {
+        unsigned long long mine;
+        const int nk = select_best(col, mine);
+        const uint32_t tb = okey_inv(static_cast<uint32_t>(mine >> 32));
+        const float s_kth = -__uint_as_float(__shfl_sync(0xffffffffu, tb, kth - 1));
+        const uint32_t arow = item.a_row0 + col;
+        if (lane == 0 && P.b_keys != nullptr && nk >= kth) {
+          const float pub = __fmaf_rn(P.b_scale, s_kth, P.b_add ? P.b_add[arow] : 0.f);
+          const int kp    = __float_as_int(pub);
+          atomicMin(P.b_keys + (P.b_idx ? P.b_idx[arow] : arow), kp >= 0 ? kp : kp ^ 0x7fffffff);
+        }
+        if (lane < KC && P.out_score != nullptr) {
+          const int64_t o = static_cast<int64_t>(item.out_off) + static_cast<int64_t>(col) * P.out_row_stride + lane;
+          P.out_score[o]  = lane < nk ? -__uint_as_float(tb) : INFINITY;
+          P.out_pos[o]    = lane < nk ? ~static_cast<uint32_t>(mine) : 0xffffffffu;
+        }
+      }
+      ptx::named_bar_sync(1, kEpiThreads);  // the next item's column init must not overtake another warp's read-out
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { ptx::tmem_dealloc<L::tmem_cols>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------ build-side kernels
+// one CTA per 128-row tile: codes [128, pq_dim] -> lane-transposed 16-byte chunks + half norms
+__global__ void __launch_bounds__(128)
+pq_stream_build_kernel(const uint8_t* __restrict__ codes, const int64_t* __restrict__ ids, int64_t pad_id, int pq_dim,
+                       const float* __restrict__ pq_centers, bool ip, uint8_t* __restrict__ stream)
+{
+  __shared__ __align__(16) uint8_t sc[128 * 64];
+  const int64_t tile = blockIdx.x;
+  const int r        = threadIdx.x;
+  const int64_t row  = tile * 128 + r;
+  const int64_t blk  = 128 * static_cast<int64_t>(pq_dim) + 512;
+  const uint8_t* src = codes + row * pq_dim;
+  float nrm = 0.f;
+  for (int j = 0; j < pq_dim; ++j) {
+    const int c = src[j];
+    sc[r * pq_dim + j] = static_cast<uint8_t>(c);
+    const float e0 = __bfloat162float(__float2bfloat16_rn(pq_centers[(static_cast<int64_t>(j) * 2 + 0) * 256 + c]));
+    const float e1 = __bfloat162float(__float2bfloat16_rn(pq_centers[(static_cast<int64_t>(j) * 2 + 1) * 256 + c]));
+    nrm = fmaf(e0, e0, nrm);
+    nrm = fmaf(e1, e1, nrm);
+  }
+  __syncthreads();
+  uint8_t* out  = stream + tile * blk;
+  const int nh  = pq_dim / 32;
+  for (int o = threadIdx.x; o < 8 * nh * 32; o += blockDim.x) {
+    const int g = o / (nh * 32), h = (o / 32) % nh, l = o % 32;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i >> 2] |= static_cast<uint32_t>(sc[(16 * g + i) * pq_dim + 32 * h + l]) << ((i & 3) * 8);
+    reinterpret_cast<uint4*>(out)[o] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  reinterpret_cast<float*>(out + 128 * pq_dim)[r] = ids[row] == pad_id ? INFINITY : (ip ? 0.f : 0.5f * nrm);
+}
+
+__global__ void pq_cb_words_kernel(const float* __restrict__ pq_centers, int pq_dim, uint32_t* __restrict__ words)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (pq_dim / 32) * 256 * 32) return;
+  const int l = t & 31, c = (t >> 5) & 255, h = t >> 13;
+  const int j = 32 * h + l;
+  const __nv_bfloat16 e0 = __float2bfloat16_rn(pq_centers[(static_cast<int64_t>(j) * 2 + 0) * 256 + c]);
+  const __nv_bfloat16 e1 = __float2bfloat16_rn(pq_centers[(static_cast<int64_t>(j) * 2 + 1) * 256 + c]);
+  words[t] = static_cast<uint32_t>(__bfloat16_as_ushort(e0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(e1)) << 16);
+}
+
+using encode_fn_t = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t get_encode_fn()
+{
+  static encode_fn_t fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_fn_t>(p);
+  });
+  B2_EXPECTS(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+// residual rows [rows, Kp] bf16, box = 64 columns x `group` rows, SWIZZLE_128B
+CUtensorMap make_query_map(const __nv_bfloat16* ptr, int64_t rows, int Kp, int group)
+{
+  CUtensorMap m;
+  cuuint64_t gdim[2]    = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Kp) * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2]     = {64, static_cast<cuuint32_t>(group)};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2_EXPECTS(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (pq residual rows) failed with code %d (rows=%lld Kp=%d)", int(r), (long long)rows, Kp);
+  return m;
+}
+
+int env_int(const char* name, int dflt)
+{
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int NQ, int NKB, int PASSES>
+void launch(cudaStream_t stream, int sms, const CUtensorMap& mq_hi, const CUtensorMap& mq_lo, pq_args a, int n_items)
+{
+  using L   = layout<NQ, NKB, PASSES>;
+  auto kern = pq_stream_scan_kernel<NQ, NKB, PASSES>;
+  a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 48) : 64;
+  const int fixed = L::off_cand + NQ * a.cap * 8 + 1024 /*alignment slack of the dynamic segment*/;
+  a.cstages = std::min(kMaxCStages, (kSmemLimit - fixed) / a.blk);
+  const int forced = env_int("CUVS_B200_PQ_CSTAGES", 0);  // limiter experiments only
+  if (forced > 0) a.cstages = std::min(a.cstages, forced);
+  B2_EXPECTS(a.cstages >= 2, "pq_stream_scan: shared memory budget exceeded (NQ=%d KC=%d passes=%d)", NQ, a.KC, PASSES);
+  const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.cstages) * a.blk;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int grid = n_items < sms ? n_items : sms;
+  timed_section ts("pq_stream_scan", stream);
+  count_launch();
+  kern<<<grid, kThreads, smem, stream>>>(mq_hi, mq_lo, a);
+  B2_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+bool pq_stream_supported(int device, int pq_dim, int pq_len, int pq_bits, bool per_subspace)
+{
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return false;
+  return major == 10 && pq_bits == 8 && per_subspace && pq_len == 2 && (pq_dim == 32 || pq_dim == 64);
+}
+
+void pq_stream_build(cudaStream_t s, const uint8_t* codes, const int64_t* ids, int64_t pad_id, int64_t rows_total, int pq_dim,
+                     const float* pq_centers, bool ip, uint8_t* stream, uint32_t* cb_words)
+{
+  B2_EXPECTS(pq_dim == 32 || pq_dim == 64, "pq_stream_build: pq_dim must be 32 or 64");
+  B2_EXPECTS(rows_total % 128 == 0, "pq_stream_build: lists must be padded to 128-row tiles");
+  count_launch();
+  pq_cb_words_kernel<<<(pq_dim / 32) * 256 * 32 / 256, 256, 0, s>>>(pq_centers, pq_dim, cb_words);
+  if (rows_total > 0) {
+    count_launch();
+    pq_stream_build_kernel<<<static_cast<unsigned>(rows_total / 128), 128, 0, s>>>(codes, ids, pad_id, pq_dim, pq_centers, ip, stream);
+  }
+  B2_CUDA(cudaGetLastError());
+}
+
+int pq_stream_group(double pairs_per_list, int KC, int passes)
+{
+  const int forced = env_int("CUVS_B200_PQ_GROUP", 0);  // tests and limiter experiments (read per call)
+  int g = pairs_per_list <= 20.0 ? 32 : (pairs_per_list <= 80.0 ? 64 : 128);
+  if (forced == 32 || forced == 64 || forced == 128) g = forced;
+  if ((KC > 16 || passes == 2) && g > 64) g = 64;  // shared-memory budget: wide candidate buffers / two residual planes
+  return g;
+}
+
+void pq_stream_scan(cudaStream_t stream, int device, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, int64_t a_rows, int Kp,
+                    const uint8_t* code_stream, const uint32_t* cb_words, int pq_dim, const tc_item* items_dev, int n_items,
+                    const int* n_items_dev, int group, int KC, int passes, float* out_score, uint32_t* out_pos, int64_t out_row_stride,
+                    const tc_bound* bound)
+{
+  if (n_items == 0) return;
+  B2_EXPECTS(Kp == 2 * pq_dim && (pq_dim == 32 || pq_dim == 64), "pq_stream_scan: pq_dim must be 32 or 64 with pq_len 2 (Kp=%d)", Kp);
+  B2_EXPECTS(KC == 16 || KC == 32, "pq_stream_scan: KC must be 16 or 32");
+  B2_EXPECTS(passes == 1 || (passes == 2 && q_lo != nullptr), "pq_stream_scan: passes must be 1, or 2 with a lo plane");
+  B2_EXPECTS(group == 32 || group == 64 || (group == 128 && KC == 16 && passes == 1), "pq_stream_scan: unsupported group %d", group);
+  B2_EXPECTS(a_rows >= group, "pq_stream_scan: the residual plane must hold at least one group of rows");
+  pq_args a{};
+  a.stream = code_stream;
+  a.cb_words = cb_words;
+  a.items = items_dev;
+  a.n_items_dev = n_items_dev;
+  a.out_score = out_score;
+  a.out_pos = out_pos;
+  a.out_row_stride = out_row_stride;
+  if (bound != nullptr && bound->keys != nullptr) {
+    a.b_keys = bound->keys;
+    a.b_idx = bound->idx;
+    a.b_add = bound->add;
+    a.b_scale = bound->scale;
+    a.kth = bound->kth;
+  } else {
+    a.b_scale = 1.0f;
+  }
+  a.n_items_host = n_items;
+  a.KC = KC;
+  a.blk = static_cast<int>(pq_stream_tile_bytes(pq_dim));
+  dbuf<int> sched(1, stream);
+  B2_CUDA(cudaMemsetAsync(sched.data(), 0, sizeof(int), stream));
+  a.sched = sched.data();
+  const CUtensorMap mq  = make_query_map(q_hi, a_rows, Kp, group);
+  const CUtensorMap mql = passes == 2 ? make_query_map(q_lo, a_rows, Kp, group) : mq;
+  const int sms = sm_count_of(device);
+  const int nkb = Kp / 64;
+#define B2_PQ_CASE(NQ_, NKB_, P_) \
+  if (group == NQ_ && nkb == NKB_ && passes == P_) return launch<NQ_, NKB_, P_>(stream, sms, mq, mql, a, n_items);
+  B2_PQ_CASE(32, 1, 1) B2_PQ_CASE(64, 1, 1) B2_PQ_CASE(128, 1, 1) B2_PQ_CASE(32, 2, 1) B2_PQ_CASE(64, 2, 1) B2_PQ_CASE(128, 2, 1)
+  B2_PQ_CASE(32, 1, 2) B2_PQ_CASE(64, 1, 2) B2_PQ_CASE(32, 2, 2) B2_PQ_CASE(64, 2, 2)
+#undef B2_PQ_CASE
+  B2_FAIL("pq_stream_scan: no kernel for group=%d Kp=%d passes=%d", group, Kp, passes);
+}
+
+}  // namespace b200

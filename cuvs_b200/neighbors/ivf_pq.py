@@ -112,6 +112,14 @@ class Index:
     def __len__(self):
         return self._i64(lib.cuvsIvfPqIndexGetSize)
 
+    def _info(self):
+        path, nbytes = C.c_int(0), C.c_int64(0)
+        check(lib.cuvsB200IvfPqIndexInfo(self._p, C.byref(path), C.byref(nbytes)))
+        return path.value, nbytes.value
+
+    streamed = property(lambda self: self._info()[0] == 2)       # served by the code-streaming scan (scan_pq.cu)
+    device_bytes = property(lambda self: self._info()[1])        # bytes of device memory the index holds
+
     def _view(self, fn, *args):
         m = DLManagedTensor()
         check(fn(self._p, *args, C.byref(m)))

@@ -8,6 +8,7 @@
 #include <cuvs/neighbors/brute_force.h>
 #include <cuvs/neighbors/cagra.h>
 #include <cuvs/neighbors/ivf_flat.h>
+#include <cuvs/neighbors/ivf_pq.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -41,6 +42,10 @@ CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t
 /* Replace the coarse centres of an (empty) index — used by the list-sharded multi-GPU build so that every rank
  * partitions the data with bit-identical centres (trained on one rank, broadcast over NCCL). centers: [n_lists, dim] f32. */
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFlatIndex_t index, DLManagedTensor* centers);
+
+/* IVF-PQ: which fine-scan kernel cuvsIvfPqSearch will use on this index by default, and the device bytes the index holds.
+ * *path: 2 = code-streaming tcgen05 scan (scan_pq.cu), 1 = decoded-row tcgen05 scan (scan_tc.cu), 0 = LUT kernel. */
+CUVS_EXPORT cuvsError_t cuvsB200IvfPqIndexInfo(cuvsIvfPqIndex_t index, int* path, int64_t* device_bytes);
 
 /* CAGRA: the graph walk is bound by random row gathers from HBM.  bits = 16 makes the index keep an fp16 copy of the
  * vectors that the walk reads instead (half the bytes); the best 32 entries of every query's final list are re-ranked

@@ -187,3 +187,95 @@ def test_wide_vectors_take_the_streamed_scan():
     assert oracle.recall_with_ties(i, d, ri, rd, eps=2e-3) >= 0.99
     gd, gi = oracle.knn(ds, qs, 10)
     assert oracle.recall(i, gi) >= 0.6  # iid-uniform 192-d data, 8 of 16 lists, 2 dims per code: PQ noise, not the scan
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reduced-precision request (lut_dtype f16 / u8) is what bench.py times: a ONE-pass tensor-core scan whose query-side
+# residual is rounded to bf16 (8-bit significand) where the reference rounds the LUT entries to fp16 / fp_8bit<5>.  These
+# tests pin that path against the oracle's LUT search run with the matching lut_dtype, BEFORE any refine:
+#   * recall_with_ties (eval_neighbours, ann_utils.cuh:257-289) at eps = 1e-2 relative: bf16 rounding of r perturbs
+#     |r - y|^2 by <= 2 |r - y| |r| 2^-9 ~ 4e-3 |r - y|^2 when |r| ~ |r - y| (the fp16 LUT's own error is ~2^-11 per entry,
+#     fp_8bit<5>'s ~2^-4: ours sits between the two);
+#   * the reference's own acceptance floors for reduced LUTs against EXACT ground truth
+#     (cpp/tests/neighbors/ann_ivf_pq.cuh:978-1064: min_recall 0.84-0.86 at pq_bits 8, fp16 / fp8 LUT variants).
+@pytest.mark.parametrize("metric", ["sqeuclidean", "inner_product"])
+@pytest.mark.parametrize("lut", ["f16", "fp8"])
+@pytest.mark.parametrize("dim,pq_dim", [(128, 64), (192, 96)])
+def test_one_pass_scan_matches_reduced_lut_oracle(metric, lut, dim, pq_dim):
+    m = _mod()
+    ds, centers = clustered(30000, dim, 5, n_centers=48)
+    qs, _ = clustered(256, dim, 6, centers=centers)
+    index = m.build(m.IndexParams(n_lists=48, pq_dim=pq_dim, metric=metric, kmeans_n_iters=10), torch.from_numpy(ds).cuda())
+    kw = {"lut_dtype": {"f16": np.float16, "fp8": np.uint8}[lut]}
+    d, i = _search(index, qs, 12, 10, "tc", **kw)
+    rd, ri = _oracle(index, qs, 12, 10, metric, lut, "f32")
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=1e-2) >= 0.99
+    # ... and it is at least as close to the fp32-LUT answer as the reference's own reduced LUT is allowed to be
+    fd, fi = _oracle(index, qs, 12, 10, metric, "f32", "f32")
+    assert oracle.recall_with_ties(i, d, fi, fd, eps=1e-2) >= 0.99
+    same = i == fi
+    assert same.mean() >= 0.9
+    np.testing.assert_allclose(d[same], fd[same], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("lut", ["f16", "fp8"])
+def test_one_pass_scan_reference_recall_floor(lut):
+    """ann_ivf_pq.cuh:26-43 defaults with the fp16 / fp8 LUT variants of :978-1064 (floor 0.84-0.86), exact ground truth."""
+    m = _mod()
+    ds = uniform(4096, 64, 1234, 0.1, 2.0)
+    qs = uniform(1024, 64, 4321, 0.1, 2.0)
+    index = m.build(m.IndexParams(n_lists=32, kmeans_trainset_fraction=1.0), torch.from_numpy(ds).cuda())
+    d, i = _search(index, qs, 20, 32, "tc", lut_dtype={"f16": np.float16, "fp8": np.uint8}[lut])
+    gd, gi = oracle.knn(ds, qs, 32)
+    assert oracle.recall_with_ties(i, d, gi, gd, eps=4e-4) >= 0.84
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The code-streaming scan (scan_pq.cu) serves pq_bits 8 / pq_len 2 / pq_dim 32|64 indexes.  Every work-item width
+# (32 / 64 / 128 probing queries as the MMA's N side), both operand depths (rot_dim 64 -> one k-block, 128 -> two), both
+# candidate-list sizes (k <= 16 -> 16 slots, k <= 32 -> 32) and both pass counts are pinned to the oracle's LUT search.
+@pytest.fixture(scope="module")
+def stream_index_128():
+    m = _mod()
+    ds, centers = clustered(40000, 128, 15, n_centers=64)
+    qs, _ = clustered(512, 128, 16, centers=centers)
+    index = m.build(m.IndexParams(n_lists=64, pq_dim=64, kmeans_n_iters=10), torch.from_numpy(ds).cuda())
+    return ds, qs, index
+
+
+@pytest.mark.parametrize("group", [32, 64, 128])
+@pytest.mark.parametrize("which,k,lut", [("d64", 10, "f16"), ("d64", 32, "f16"), ("d128", 10, "f16"), ("d128", 32, "f32"), ("d128", 10, "f32")])
+def test_streamed_scan_all_shapes(small_index, stream_index_128, group, which, k, lut):
+    ds, qs, index = small_index if which == "d64" else stream_index_128
+    assert index.streamed, "pq_bits 8 / pq_len 2 / pq_dim 32|64 must be served by the code-streaming scan"
+    os.environ["CUVS_B200_PQ_GROUP"] = str(group)
+    try:
+        kw = {} if lut == "f32" else {"lut_dtype": np.float16}
+        d, i = _search(index, qs, 8, k, "tc", **kw)
+    finally:
+        del os.environ["CUVS_B200_PQ_GROUP"]
+    rd, ri = _oracle(index, qs, 8, k, "sqeuclidean", lut, "f32")
+    eps = 2e-3 if lut == "f32" else 1e-2
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=eps) >= 0.99
+    # returned ids are unique per query and really belong to the probed lists' rows (no padding rows, no garbage)
+    assert all(len(set(r.tolist())) == k for r in i) and (i >= 0).all() and (i < len(ds)).all()
+
+
+def test_streamed_index_keeps_no_decoded_rows(stream_index_128):
+    ds, qs, index = stream_index_128
+    assert index.streamed
+    # codes (64 B) + code stream (68 B) + ids (8 B) per vector, padded lists, + quantizers: well under the 288 B/vector
+    # the decoded-row layout alone would take
+    assert index.device_bytes < len(ds) * 200
+
+
+def test_streamed_scan_empty_and_tiny_lists():
+    """n_lists close to n: lists of 0..3 rows, every tile almost entirely padding; probes of empty lists are dropped."""
+    m = _mod()
+    ds = uniform(300, 64, 5, -1, 1)
+    qs = uniform(40, 64, 6, -1, 1)
+    index = m.build(m.IndexParams(n_lists=128, pq_dim=32, kmeans_n_iters=4, kmeans_trainset_fraction=1.0), torch.from_numpy(ds).cuda())
+    assert index.streamed
+    d, i = _search(index, qs, 128, 10, "tc", lut_dtype=np.float16)
+    rd, ri = _oracle(index, qs, 128, 10, "sqeuclidean", "f16", "f32")
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=1e-2) >= 0.99
