@@ -278,10 +278,11 @@ class IvfPqWorkload:
     timing_section = "pq_scan"
 
     def __init__(self, n=100_000_000, d=128, nq=10_000, k=10, n_lists=16384, pq_dim=64, n_probes=48, refine_ratio=2, seed=1234,
-                 rank=0, world=1, lut_dtype="f16", data_rank=16):
+                 rank=0, world=1, lut_dtype="f16", data_rank=16, resources=None):
         from cuvs_b200.neighbors import brute_force, ivf_pq, refine
         self.n, self.d, self.nq, self.k = n, d, nq, k
         self.rank, self.world = rank, world
+        self._res = resources
         self.n_lists, self.pq_dim, self.n_probes, self.refine_ratio = n_lists, pq_dim, n_probes, refine_ratio
         self.data_rank = data_rank
         self.name = (f"ivf_pq {n // 1_000_000}M x {d} f32, n_lists={n_lists} pq_dim={pq_dim} pq_bits=8 n_probes={n_probes}, "
@@ -321,7 +322,7 @@ class IvfPqWorkload:
         rows whose IVF list it owns (list % world == rank).  No inter-rank movement of vectors (cuvs_b200/distributed.py)."""
         import torch.distributed as dist
         from cuvs_b200.cluster import kmeans
-        from cuvs_b200.distributed import ShardedIvfFlat, owner_of_list
+        from cuvs_b200.distributed import Comm, ShardedIvfFlat, owner_of_list
         pq = self.pq
         p0 = pq.IndexParams(n_lists=self.n_lists, pq_dim=self.pq_dim, pq_bits=8, kmeans_n_iters=10, add_data_on_build=False)
         proto = pq.build(p0, self.dataset)
@@ -345,15 +346,15 @@ class IvfPqWorkload:
                 self.refine(self.dataset, q, self.cand, indices=self.neighbors, distances=self.distances, resources=res)
             else:
                 pq.search(sp, local, q, k, neighbors=self.neighbors, distances=self.distances, resources=res)
-            res.sync()
-            return self.distances, self.neighbors
+            return self.distances, self.neighbors  # (no host sync: the exchange step is enqueued on the same stream)
 
-        return index, ShardedIvfFlat(index, local_search=local_search)
+        comm = Comm(self._res) if self._res is not None else None
+        return index, ShardedIvfFlat(index, local_search=local_search, comm=comm)
 
     def _search(self, q, res):
         if self.sharded is not None:
             self._res = res
-            d, i = self.sharded.search(self.sp, q, self.k)
+            d, i = self.sharded.search(self.sp, q, self.k, resources=res)
             self.final_d, self.final_i = d, i
             return
         if self.refine_ratio > 1:
@@ -530,7 +531,7 @@ class IvfFlatWorkload:
     dtype = "bf16 tensor-core list scan (1 pass), fp32 accumulate; exact fp32 re-score of the candidates"
     timing_section = "ivf_flat_scan"
 
-    def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=4096, n_probes=64, seed=1234, rank=0, world=1):
+    def __init__(self, n=10_000_000, d=128, nq=10_000, k=10, n_lists=4096, n_probes=64, seed=1234, rank=0, world=1, resources=None):
         from cuvs_b200.neighbors import ivf_flat
         from cuvs_b200.distributed import ShardedIvfFlat, build_sharded_ivf_flat
         self.n, self.d, self.nq, self.k, self.n_lists, self.n_probes = n, d, nq, k, n_lists, n_probes
@@ -549,7 +550,7 @@ class IvfFlatWorkload:
             ids = torch.arange(n, dtype=torch.int64, device="cuda")
             chunks = ((self.dataset[s:s + step], ids[s:s + step]) for s in range(0, n, step))
             n_train = int(max(2_000_000, 128 * n_lists))
-            self.sharded = build_sharded_ivf_flat(params, self.dataset[:: max(1, n // n_train)].contiguous(), chunks)
+            self.sharded = build_sharded_ivf_flat(params, self.dataset[:: max(1, n // n_train)].contiguous(), chunks, resources=resources)
             self.index = self.sharded.local
         torch.cuda.synchronize()
         self.build_s = time.time() - t0
@@ -694,8 +695,10 @@ def run_ours(args):
         if args.degree:
             kw["degree"] = args.degree
         kw["walk_bits"] = args.walk_bits
-    wl = WORKLOADS[args.workload](**kw)
     res = Resources()
+    if args.workload in ("ivf_pq", "ivf_pq_c2", "ivf_flat"):
+        kw["resources"] = res
+    wl = WORKLOADS[args.workload](**kw)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():

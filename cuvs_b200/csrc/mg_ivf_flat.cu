@@ -1,17 +1,23 @@
 // Single-process multi-GPU IVF-Flat (cuvsMultiGpuIvfFlat*) and dense pairwise distance.
 //
-// Reference: cpp/src/neighbors/mg/snmg.cuh:92-707 (replicated / row-sharded index, OpenMP thread per GPU, NCCL
-// send/recv to a root + knn_merge_parts), c/src/neighbors/mg_ivf_flat.cpp.  This entry point keeps the reference's
-// contract (HOST queries / outputs, row-sharded or replicated) for bindings that use it; the B200-native sharding
-// (by IVF list, one process per GPU, NCCL all-gather) lives in cuvs_b200/distributed.py — see DESIGN.md §7.
-// Here every device runs the ordinary per-device C entry points on its own stream; the per-shard partials are
-// merged on the host (the payload is nq*k*12 bytes per shard).
+// Reference: cpp/src/neighbors/mg/snmg.cuh:92-707 (replicated / row-sharded index, OpenMP thread per GPU, ncclSend/ncclRecv
+// of the partials to a root + knn_merge_parts on the root, results through the host), c/src/neighbors/mg_ivf_flat.cpp.
+// Same C contract (HOST dataset / queries / outputs, handle from cuvsMultiGpuResourcesCreate), B200 data plan:
+//   SHARDED     the index is sharded by IVF LIST (BASELINE north_star): one set of coarse centres trained on device 0 and
+//               installed on every device, list l lives on device l % n_devices with GLOBAL row ids; a search sends the
+//               whole query batch to every device, each scans the probed lists it owns, and the partial top-k are
+//               exchanged by ONE grouped ncclAllGather over NVLink (comm.cu) and merged on device 0 — no host merge,
+//               no id translation, one D2H of the final [nq, k] result.
+//   REPLICATED  every device holds the full index; the query batch is split across devices (no exchange step).
+#include "comm.cuh"
 #include "common.hpp"
 #include "exact.cuh"
 #include "timing.hpp"
 
+#include <cuvs/cluster/kmeans.h>
 #include <cuvs/distance/pairwise_distance.h>
 #include <cuvs/neighbors/mg_ivf_flat.h>
+#include <cuvs_b200/ext.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -33,8 +39,10 @@ struct mg_index {
   cuvsDistanceType metric = L2Expanded;
   int dim = 0;
   std::vector<mg_shard> shards;
+  comm_group* comm = nullptr;  // SHARDED: NCCL communicators over the handle's devices
   ~mg_index()
   {
+    if (comm) destroy_comm_group(comm);
     int cur = 0;
     cudaGetDevice(&cur);
     for (auto& s : shards) {
@@ -127,22 +135,127 @@ cuvsError_t cuvsMultiGpuIvfFlatBuild(cuvsResources_t res, cuvsMultiGpuIvfFlatInd
     mg->metric  = params->base_params->metric;
     mg->dim     = static_cast<int>(ds.shape[1]);
     const int64_t n = ds.shape[0];
+    const int d     = mg->dim;
     const int nd    = static_cast<int>(r->mg_devices.size());
+    const float* x  = dl_ptr<float>(ds);
+    const bool sharded = mg->mode == CUVS_NEIGHBORS_MG_SHARDED && nd > 1;
     for (int i = 0; i < nd; ++i) {
       mg_shard sh;
       sh.device = r->mg_devices[i];
-      sh.row0   = mg->mode == CUVS_NEIGHBORS_MG_SHARDED ? n * i / nd : 0;
-      sh.rows   = mg->mode == CUVS_NEIGHBORS_MG_SHARDED ? n * (i + 1) / nd - sh.row0 : n;
+      sh.row0   = 0;
+      sh.rows   = n;
       device_guard g(sh.device);
       check_c(cuvsResourcesCreate(&sh.res), "cuvsResourcesCreate");
       check_c(cuvsStreamSet(sh.res, r->mg_streams[i]), "cuvsStreamSet");
       check_c(cuvsIvfFlatIndexCreate(&sh.index), "cuvsIvfFlatIndexCreate");
-      cuvsIvfFlatIndexParams p = *params->base_params;
-      p.n_lists = static_cast<uint32_t>(std::max<int64_t>(1, std::min<int64_t>(p.n_lists, sh.rows)));
-      int64_t shape[2] = {sh.rows, mg->dim};
-      DLManagedTensor part = make_dl(dl_ptr<float>(ds) + sh.row0 * mg->dim, kDLCPU, 0, ds.dtype, 2, shape);
       mg->shards.push_back(sh);
-      check_c(cuvsIvfFlatBuild(sh.res, &p, &part, sh.index), "cuvsIvfFlatBuild (shard)");
+    }
+    cuvsIvfFlatIndexParams p = *params->base_params;
+    p.n_lists                = static_cast<uint32_t>(std::max<int64_t>(1, std::min<int64_t>(p.n_lists, n)));
+    if (!sharded) {
+      // REPLICATED (or a single device): the full index on every device
+      for (int i = 0; i < nd; ++i) {
+        device_guard g(mg->shards[i].device);
+        int64_t shape[2] = {n, d};
+        DLManagedTensor full = make_dl(const_cast<float*>(x), kDLCPU, 0, ds.dtype, 2, shape);
+        check_c(cuvsIvfFlatBuild(mg->shards[i].res, &p, &full, mg->shards[i].index), "cuvsIvfFlatBuild (replica)");
+      }
+    } else {
+      // SHARDED by IVF list.  (1) train the coarse centres once, on device 0, on the build's usual subsample.
+      cuvsIvfFlatIndexParams p0 = p;
+      p0.add_data_on_build      = false;
+      std::vector<float> centers(static_cast<size_t>(p.n_lists) * d);
+      {
+        device_guard g(mg->shards[0].device);
+        int64_t shape[2] = {n, d};
+        DLManagedTensor full = make_dl(const_cast<float*>(x), kDLCPU, 0, ds.dtype, 2, shape);
+        check_c(cuvsIvfFlatBuild(mg->shards[0].res, &p0, &full, mg->shards[0].index), "cuvsIvfFlatBuild (train)");
+        DLManagedTensor cv{};
+        check_c(cuvsIvfFlatIndexGetCenters(mg->shards[0].index, &cv), "cuvsIvfFlatIndexGetCenters");
+        B2_CUDA(cudaMemcpyAsync(centers.data(), cv.dl_tensor.data, centers.size() * sizeof(float), cudaMemcpyDeviceToHost, r->mg_streams[0]));
+        B2_CUDA(cudaStreamSynchronize(r->mg_streams[0]));
+      }
+      // (2) every other device: an empty index with the SAME centres (bit-identical partition rule everywhere)
+      for (int i = 1; i < nd; ++i) {
+        device_guard g(mg->shards[i].device);
+        int64_t shape[2] = {static_cast<int64_t>(p.n_lists), d};
+        DLManagedTensor seed = make_dl(centers.data(), kDLCPU, 0, ds.dtype, 2, shape);
+        cuvsIvfFlatIndexParams pi = p0;
+        pi.kmeans_n_iters           = 1;
+        pi.kmeans_trainset_fraction = 1.0;
+        check_c(cuvsIvfFlatBuild(mg->shards[i].res, &pi, &seed, mg->shards[i].index), "cuvsIvfFlatBuild (empty shard)");
+        check_c(cuvsB200IvfFlatSetCenters(mg->shards[i].res, mg->shards[i].index, &seed), "cuvsB200IvfFlatSetCenters");
+      }
+      // (3) label the rows chunk by chunk on device 0 and route every row to the owner of its list (list % n_devices)
+      //     with its GLOBAL row id
+      cuvsKMeansParams_t kp;
+      check_c(cuvsKMeansParamsCreate(&kp), "cuvsKMeansParamsCreate");
+      kp->n_clusters = static_cast<int>(p.n_lists);
+      kp->metric     = mg->metric == InnerProduct ? InnerProduct : L2Expanded;
+      const int64_t chunk = std::max<int64_t>(1, (int64_t(1) << 26) / d);  // 256 MiB of rows per step
+      std::vector<int> labels(static_cast<size_t>(std::min(chunk, n)));
+      std::vector<std::vector<float>> rows_of(nd);
+      std::vector<std::vector<int64_t>> ids_of(nd);
+      float *d_x = nullptr, *d_c = nullptr;
+      int* d_l = nullptr;
+      {
+        device_guard g(mg->shards[0].device);
+        auto st = r->mg_streams[0];
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_x), sizeof(float) * std::min(chunk, n) * d, st));
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_c), sizeof(float) * centers.size(), st));
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_l), sizeof(int) * std::min(chunk, n), st));
+        B2_CUDA(cudaMemcpyAsync(d_c, centers.data(), sizeof(float) * centers.size(), cudaMemcpyHostToDevice, st));
+      }
+      for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t rows = std::min(chunk, n - r0);
+        {
+          device_guard g(mg->shards[0].device);
+          auto st = r->mg_streams[0];
+          B2_CUDA(cudaMemcpyAsync(d_x, x + r0 * d, sizeof(float) * rows * d, cudaMemcpyHostToDevice, st));
+          int64_t xs[2] = {rows, d}, cs[2] = {static_cast<int64_t>(p.n_lists), d}, ls[1] = {rows};
+          DLManagedTensor tx = make_dl(d_x, kDLCUDA, mg->shards[0].device, DLDataType{kDLFloat, 32, 1}, 2, xs);
+          DLManagedTensor tc = make_dl(d_c, kDLCUDA, mg->shards[0].device, DLDataType{kDLFloat, 32, 1}, 2, cs);
+          DLManagedTensor tl = make_dl(d_l, kDLCUDA, mg->shards[0].device, DLDataType{kDLInt, 32, 1}, 1, ls);
+          double inertia = 0;
+          check_c(cuvsKMeansPredict(mg->shards[0].res, kp, &tx, nullptr, &tc, &tl, false, &inertia), "cuvsKMeansPredict (routing)");
+          B2_CUDA(cudaMemcpyAsync(labels.data(), d_l, sizeof(int) * rows, cudaMemcpyDeviceToHost, st));
+          B2_CUDA(cudaStreamSynchronize(st));
+        }
+        for (int i = 0; i < nd; ++i) { rows_of[i].clear(); ids_of[i].clear(); }
+        for (int64_t j = 0; j < rows; ++j) {
+          const int owner = labels[j] % nd;
+          rows_of[owner].insert(rows_of[owner].end(), x + (r0 + j) * d, x + (r0 + j + 1) * d);
+          ids_of[owner].push_back(r0 + j);
+        }
+        for (int i = 0; i < nd; ++i) {
+          const int64_t m = static_cast<int64_t>(ids_of[i].size());
+          if (m == 0) continue;
+          device_guard g(mg->shards[i].device);
+          auto st = r->mg_streams[i];
+          float* dv = nullptr;
+          int64_t* di = nullptr;
+          B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dv), sizeof(float) * m * d, st));
+          B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&di), sizeof(int64_t) * m, st));
+          B2_CUDA(cudaMemcpyAsync(dv, rows_of[i].data(), sizeof(float) * m * d, cudaMemcpyHostToDevice, st));
+          B2_CUDA(cudaMemcpyAsync(di, ids_of[i].data(), sizeof(int64_t) * m, cudaMemcpyHostToDevice, st));
+          int64_t vs[2] = {m, d}, is[1] = {m};
+          DLManagedTensor tv = make_dl(dv, kDLCUDA, mg->shards[i].device, DLDataType{kDLFloat, 32, 1}, 2, vs);
+          DLManagedTensor ti = make_dl(di, kDLCUDA, mg->shards[i].device, DLDataType{kDLInt, 64, 1}, 1, is);
+          check_c(cuvsIvfFlatExtend(mg->shards[i].res, &tv, &ti, mg->shards[i].index), "cuvsIvfFlatExtend (shard)");
+          B2_CUDA(cudaFreeAsync(dv, st));
+          B2_CUDA(cudaFreeAsync(di, st));
+          B2_CUDA(cudaStreamSynchronize(st));  // the host staging vectors are reused by the next chunk
+        }
+      }
+      {
+        device_guard g(mg->shards[0].device);
+        auto st = r->mg_streams[0];
+        B2_CUDA(cudaFreeAsync(d_x, st));
+        B2_CUDA(cudaFreeAsync(d_c, st));
+        B2_CUDA(cudaFreeAsync(d_l, st));
+      }
+      check_c(cuvsKMeansParamsDestroy(kp), "cuvsKMeansParamsDestroy");
+      mg->comm = make_local_comm_group(r->mg_devices);
     }
     if (index->addr) delete reinterpret_cast<mg_index*>(index->addr);
     index->addr  = reinterpret_cast<uintptr_t>(mg.release());
@@ -166,69 +279,65 @@ cuvsError_t cuvsMultiGpuIvfFlatSearch(cuvsResources_t res, cuvsMultiGpuIvfFlatSe
     const int k      = static_cast<int>(nb.shape[1]);
     const int ns     = static_cast<int>(mg.shards.size());
     const bool select_min = mg.metric != InnerProduct;
-    struct part { float* dq = nullptr; int64_t* di = nullptr; float* dv = nullptr; std::vector<int64_t> hi; std::vector<float> hv; int64_t q0 = 0, qn = 0; };
+    const bool sharded    = mg.comm != nullptr;
+    struct part { float* dq = nullptr; int64_t* di = nullptr; float* dv = nullptr; int64_t q0 = 0, qn = 0; cudaStream_t st = nullptr; };
     std::vector<part> parts(ns);
-    // launch everything asynchronously on each device's stream, then collect
+    int64_t* out_i = dl_ptr<int64_t>(nb);
+    float* out_v   = dl_ptr<float>(dd);
+    // every device: queries in (the whole batch when sharded, a slice when replicated), local search on its own stream
     for (int s = 0; s < ns; ++s) {
       auto& sh = mg.shards[s];
       auto& pt = parts[s];
-      if (mg.mode == CUVS_NEIGHBORS_MG_SHARDED) { pt.q0 = 0; pt.qn = nq; }
+      if (sharded) { pt.q0 = 0; pt.qn = nq; }
       else { pt.q0 = nq * s / ns; pt.qn = nq * (s + 1) / ns - pt.q0; }
-      if (pt.qn == 0) continue;
       device_guard g(sh.device);
-      cudaStream_t st;
-      check_c(cuvsStreamGet(sh.res, &st), "cuvsStreamGet");
-      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.dq), sizeof(float) * pt.qn * mg.dim, st));
-      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.di), sizeof(int64_t) * pt.qn * k, st));
-      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.dv), sizeof(float) * pt.qn * k, st));
-      B2_CUDA(cudaMemcpyAsync(pt.dq, dl_ptr<float>(q) + pt.q0 * mg.dim, sizeof(float) * pt.qn * mg.dim, cudaMemcpyHostToDevice, st));
+      check_c(cuvsStreamGet(sh.res, &pt.st), "cuvsStreamGet");
+      if (pt.qn == 0) continue;
+      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.dq), sizeof(float) * pt.qn * mg.dim, pt.st));
+      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.di), sizeof(int64_t) * pt.qn * k, pt.st));
+      B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pt.dv), sizeof(float) * pt.qn * k, pt.st));
+      B2_CUDA(cudaMemcpyAsync(pt.dq, dl_ptr<float>(q) + pt.q0 * mg.dim, sizeof(float) * pt.qn * mg.dim, cudaMemcpyHostToDevice, pt.st));
       int64_t qs[2] = {pt.qn, mg.dim}, os[2] = {pt.qn, k};
       DLManagedTensor tq = make_dl(pt.dq, kDLCUDA, sh.device, DLDataType{kDLFloat, 32, 1}, 2, qs);
       DLManagedTensor ti = make_dl(pt.di, kDLCUDA, sh.device, DLDataType{kDLInt, 64, 1}, 2, os);
       DLManagedTensor tv = make_dl(pt.dv, kDLCUDA, sh.device, DLDataType{kDLFloat, 32, 1}, 2, os);
       check_c(cuvsIvfFlatSearch(sh.res, params->base_params, sh.index, &tq, &ti, &tv, cuvsFilter{0, NO_FILTER}), "cuvsIvfFlatSearch (shard)");
-      pt.hi.resize(static_cast<size_t>(pt.qn) * k);
-      pt.hv.resize(static_cast<size_t>(pt.qn) * k);
-      B2_CUDA(cudaMemcpyAsync(pt.hi.data(), pt.di, sizeof(int64_t) * pt.qn * k, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaMemcpyAsync(pt.hv.data(), pt.dv, sizeof(float) * pt.qn * k, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaFreeAsync(pt.dq, st));
-      B2_CUDA(cudaFreeAsync(pt.di, st));
-      B2_CUDA(cudaFreeAsync(pt.dv, st));
+      if (!sharded) {
+        B2_CUDA(cudaMemcpyAsync(out_i + pt.q0 * k, pt.di, sizeof(int64_t) * pt.qn * k, cudaMemcpyDeviceToHost, pt.st));
+        B2_CUDA(cudaMemcpyAsync(out_v + pt.q0 * k, pt.dv, sizeof(float) * pt.qn * k, cudaMemcpyDeviceToHost, pt.st));
+      }
+    }
+    if (sharded && nq > 0) {
+      // the one exchange step: grouped ncclAllGather of the packed partial top-k over NVLink, k-way merge on device 0
+      std::vector<cudaStream_t> streams(ns);
+      std::vector<const float*> pd(ns);
+      std::vector<const int64_t*> pi(ns);
+      std::vector<float*> od(ns, nullptr);
+      std::vector<int64_t*> oi(ns, nullptr);
+      for (int s = 0; s < ns; ++s) { streams[s] = parts[s].st; pd[s] = parts[s].dv; pi[s] = parts[s].di; }
+      float* m_v   = nullptr;
+      int64_t* m_i = nullptr;
+      {
+        device_guard g(mg.shards[0].device);
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&m_v), sizeof(float) * nq * k, parts[0].st));
+        B2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&m_i), sizeof(int64_t) * nq * k, parts[0].st));
+      }
+      od[0] = m_v;
+      oi[0] = m_i;
+      allgather_merge_topk_all(*mg.comm, streams, pd, pi, nq, k, select_min, od, oi, 0);
+      device_guard g(mg.shards[0].device);
+      B2_CUDA(cudaMemcpyAsync(out_i, m_i, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, parts[0].st));
+      B2_CUDA(cudaMemcpyAsync(out_v, m_v, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, parts[0].st));
+      B2_CUDA(cudaFreeAsync(m_v, parts[0].st));
+      B2_CUDA(cudaFreeAsync(m_i, parts[0].st));
     }
     for (int s = 0; s < ns; ++s) {
       device_guard g(mg.shards[s].device);
-      check_c(cuvsStreamSync(mg.shards[s].res), "cuvsStreamSync");
-    }
-    int64_t* out_i = dl_ptr<int64_t>(nb);
-    float* out_v   = dl_ptr<float>(dd);
-    if (mg.mode != CUVS_NEIGHBORS_MG_SHARDED) {
-      for (int s = 0; s < ns; ++s) {
-        auto& pt = parts[s];
-        if (!pt.qn) continue;
-        std::copy(pt.hi.begin(), pt.hi.end(), out_i + pt.q0 * k);
-        std::copy(pt.hv.begin(), pt.hv.end(), out_v + pt.q0 * k);
-      }
-      return;
-    }
-    // k-way merge of the sorted per-shard lists, ids translated by the shard's row offset (snmg.cuh:346-356)
-    std::vector<int> cur(ns);
-    for (int64_t qi = 0; qi < nq; ++qi) {
-      std::fill(cur.begin(), cur.end(), 0);
-      for (int j = 0; j < k; ++j) {
-        int best = -1;
-        float bv = 0;
-        for (int s = 0; s < ns; ++s) {
-          if (cur[s] >= k) continue;
-          const int64_t id = parts[s].hi[qi * k + cur[s]];
-          if (id == INT64_MAX || id < 0) { cur[s] = k; continue; }
-          const float v = parts[s].hv[qi * k + cur[s]];
-          if (best < 0 || (select_min ? v < bv : v > bv)) { best = s; bv = v; }
-        }
-        if (best < 0) { out_i[qi * k + j] = INT64_MAX; out_v[qi * k + j] = select_min ? FLT_MAX : -FLT_MAX; continue; }
-        out_i[qi * k + j] = parts[best].hi[qi * k + cur[best]] + mg.shards[best].row0;
-        out_v[qi * k + j] = bv;
-        ++cur[best];
-      }
+      auto& pt = parts[s];
+      if (pt.dq) B2_CUDA(cudaFreeAsync(pt.dq, pt.st));
+      if (pt.di) B2_CUDA(cudaFreeAsync(pt.di, pt.st));
+      if (pt.dv) B2_CUDA(cudaFreeAsync(pt.dv, pt.st));
+      check_c(cuvsStreamSync(mg.shards[s].res), "cuvsStreamSync");  // host outputs are complete when the call returns
     }
   });
 }

@@ -43,11 +43,54 @@ def _default_merge(keys: torch.Tensor, vals: torch.Tensor, n_parts: int, k: int,
     return ok, ov
 
 
+class Comm:
+    """The library's own NCCL communicator (csrc/comm.cu): one per process/GPU.  Bootstrapped over an existing
+    torch.distributed group — rank 0 makes the ncclUniqueId inside the library, the 128 bytes are broadcast, every rank calls
+    cuvsB200CommCreate.  After that the exchange step of a sharded search runs entirely inside libcuvs_c.so on the
+    resource's stream (pack -> ONE ncclAllGather -> k-way merge), with no host synchronisation."""
+
+    def __init__(self, resources, group=None):
+        import ctypes as C
+
+        from ._capi import check, lib
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        ident = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            check(lib.cuvsB200NcclUniqueId(ident))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self._p = C.c_void_p()
+        check(lib.cuvsB200CommCreate(resources.get_c_obj(), ident, C.c_int(self.rank), C.c_int(self.world), C.byref(self._p)))
+
+    def allgather_merge(self, resources, d, i, out_d, out_i, select_min=True):
+        import ctypes as C
+
+        from ._capi import DL, check, lib
+        check(lib.cuvsB200AllGatherMergeTopK(resources.get_c_obj(), self._p, DL(d).ptr, DL(i).ptr, DL(out_d).ptr, DL(out_i).ptr,
+                                             C.c_bool(select_min)))
+
+    def __del__(self):
+        try:
+            from ._capi import lib
+            if self._p:
+                lib.cuvsB200CommDestroy(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
 class ShardedIvfFlat:
-    """A list-sharded IVF-Flat index: `local` holds the lists this rank owns (all other lists are empty)."""
+    """A list-sharded IVF index: `local` holds the lists this rank owns (all other lists are empty).
+
+    comm: a `Comm` (the library's NCCL communicator) — the exchange step then runs inside libcuvs_c.so on the resource's
+    stream.  Without one (CPU tests over gloo; `local_search=` / `merge=` hooks) the same layout is exchanged with
+    torch.distributed collectives."""
 
     def __init__(self, local_index, group=None, select_min: bool = True,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, comm: Optional["Comm"] = None):
         self.local = local_index
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -55,6 +98,8 @@ class ShardedIvfFlat:
         self.select_min = select_min
         self._local_search = local_search
         self._merge = merge or _default_merge
+        self.comm = comm
+        self._out = None
 
     def search(self, search_params, queries, k, resources=None):
         """Every rank passes the same `queries`; returns (distances [nq,k], global ids [nq,k]) — identical on all ranks."""
@@ -66,6 +111,11 @@ class ShardedIvfFlat:
         if self.world == 1:
             return d, i
         nq = d.shape[0]
+        if self.comm is not None and resources is not None:
+            if self._out is None or self._out[0].shape != d.shape:
+                self._out = (torch.empty_like(d), torch.empty_like(i))
+            self.comm.allgather_merge(resources, d, i, self._out[0], self._out[1], self.select_min)
+            return self._out
         keys = torch.empty((self.world * nq, k), dtype=d.dtype, device=d.device)
         vals = torch.empty((self.world * nq, k), dtype=i.dtype, device=i.device)
         # the one exchange step: all-gather of the partial top-k (part-major layout = what knn_merge_parts takes)
@@ -100,4 +150,5 @@ def build_sharded_ivf_flat(index_params, train_rows: torch.Tensor, chunks, group
         mine = owner_of_list(labels.to(torch.int64), world) == rank
         if bool(mine.any()):
             ivf_flat.extend(index, rows[mine].contiguous(), ids[mine].contiguous(), resources=resources)
-    return ShardedIvfFlat(index, group=group)
+    comm = Comm(resources, group) if (world > 1 and resources is not None and dist.get_backend(group) == "nccl") else None
+    return ShardedIvfFlat(index, group=group, comm=comm)

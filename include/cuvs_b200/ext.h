@@ -9,6 +9,7 @@
 #include <cuvs/neighbors/cagra.h>
 #include <cuvs/neighbors/ivf_flat.h>
 #include <cuvs/neighbors/ivf_pq.h>
+#include <stdbool.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -46,6 +47,24 @@ CUVS_EXPORT cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFl
 /* IVF-PQ: which fine-scan kernel cuvsIvfPqSearch will use on this index by default, and the device bytes the index holds.
  * *path: 2 = code-streaming tcgen05 scan (scan_pq.cu), 1 = decoded-row tcgen05 scan (scan_tc.cu), 0 = LUT kernel. */
 CUVS_EXPORT cuvsError_t cuvsB200IvfPqIndexInfo(cuvsIvfPqIndex_t index, int* path, int64_t* device_bytes);
+
+/* ---- multi-GPU exchange step (one process per GPU) ------------------------------------------------
+ * The index is sharded by IVF list: every rank searches the lists it owns for the whole query batch and holds a partial
+ * top-k [n_queries, k] with GLOBAL ids.  cuvsB200AllGatherMergeTopK enqueues, on the handle's stream, ONE ncclAllGather of
+ * the packed partials (n_queries*k*12 bytes per rank) and the k-way merge; the merged result is identical on all ranks.
+ * No host synchronisation.  Bootstrap: rank 0 calls cuvsB200NcclUniqueId, the 128 bytes travel to the other ranks by any
+ * means (torch.distributed broadcast, MPI, a file), every rank calls cuvsB200CommCreate.  NCCL is dlopen'ed on first use. */
+typedef struct cuvsB200Comm* cuvsB200Comm_t;
+CUVS_EXPORT cuvsError_t cuvsB200NcclUniqueId(void* id128);
+CUVS_EXPORT cuvsError_t cuvsB200CommCreate(cuvsResources_t res, const void* id128, int rank, int world, cuvsB200Comm_t* comm);
+CUVS_EXPORT cuvsError_t cuvsB200CommDestroy(cuvsB200Comm_t comm);
+CUVS_EXPORT cuvsError_t cuvsB200AllGatherMergeTopK(cuvsResources_t res,
+                                                   cuvsB200Comm_t comm,
+                                                   DLManagedTensor* distances,     /* [n_queries, k] f32, this rank's partial */
+                                                   DLManagedTensor* neighbors,     /* [n_queries, k] i64, global ids */
+                                                   DLManagedTensor* out_distances, /* [n_queries, k] f32 */
+                                                   DLManagedTensor* out_neighbors, /* [n_queries, k] i64 */
+                                                   bool select_min);
 
 /* CAGRA: the graph walk is bound by random row gathers from HBM.  bits = 16 makes the index keep an fp16 copy of the
  * vectors that the walk reads instead (half the bytes); the best 32 entries of every query's final list are re-ranked
