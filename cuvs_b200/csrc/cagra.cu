@@ -25,6 +25,9 @@
 #include "common.hpp"
 #include <cuda_fp16.h>
 #include <cuvs_b200/ext.h>
+#include <library_types.h>
+
+#include "npy_io.hpp"
 #include "exact.cuh"
 #include "select_k.cuh"
 #include "timing.hpp"
@@ -989,7 +992,11 @@ cuvsError_t cuvsCagraSearch(cuvsResources_t res, cuvsCagraSearchParams_t params,
   });
 }
 
-// Own container (version 1): header, graph, optional dataset.
+// cuVS index file, serialization version 5 (cpp/src/neighbors/detail/cagra/cagra_serialize.cuh:30-85, :270-320; dataset
+// records cpp/src/neighbors/detail/dataset_serialize.hpp:30-200): the 4-byte dtype tag "<f4\0", then NPY records
+// (npy_io.hpp) — version i4 = 5, size u4, dim u4, graph_degree u4, metric i4, graph u4 [size, graph_degree],
+// content_map u4 (bit 0: dataset follows, bit 1: source indices follow); dataset = instance tag u4 (1 empty: suggested_dim
+// u4 | 2 strided: cudaDataType u4, n_rows i8, dim u4, stride u4, data [n_rows, dim] without the row padding).
 cuvsError_t cuvsCagraSerialize(cuvsResources_t res, const char* filename, cuvsCagraIndex_t index, bool include_dataset)
 {
   return guarded([=] {
@@ -999,17 +1006,27 @@ cuvsError_t cuvsCagraSerialize(cuvsResources_t res, const char* filename, cuvsCa
     B2_EXPECTS(bool(os), "Cannot open file %s", filename);
     const char tag[4] = {'<', 'f', '4', 0};
     os.write(tag, 4);
-    int64_t hdr[6] = {1, static_cast<int64_t>(idx.metric), idx.n, idx.dim, idx.degree, include_dataset ? 1 : 0};
-    os.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+    npy::write_scalar<int32_t>(os, 5);
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.n));
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.dim));
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.degree));
+    npy::write_scalar<int32_t>(os, static_cast<int32_t>(idx.metric));
     std::vector<uint32_t> g(static_cast<size_t>(idx.n) * idx.degree);
     B2_CUDA(cudaMemcpyAsync(g.data(), idx.graph, g.size() * 4, cudaMemcpyDeviceToHost, r->stream));
     B2_CUDA(cudaStreamSynchronize(r->stream));
-    os.write(reinterpret_cast<const char*>(g.data()), static_cast<std::streamsize>(g.size() * 4));
-    if (include_dataset) {
+    npy::write_array<uint32_t>(os, g.data(), {idx.n, idx.degree});
+    const bool with_data = include_dataset && idx.n > 0 && idx.data != nullptr;
+    npy::write_scalar<uint32_t>(os, with_data ? 1u : 0u);
+    if (with_data) {
+      npy::write_scalar<uint32_t>(os, 2u);                       // kSerializeStridedDataset
+      npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(CUDA_R_32F));
+      npy::write_scalar<int64_t>(os, idx.n);
+      npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.dim));
+      npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.ld));
       std::vector<float> d(static_cast<size_t>(idx.n) * idx.dim);
       B2_CUDA(cudaMemcpy2DAsync(d.data(), sizeof(float) * idx.dim, idx.data, sizeof(float) * idx.ld, sizeof(float) * idx.dim, idx.n, cudaMemcpyDeviceToHost, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
-      os.write(reinterpret_cast<const char*>(d.data()), static_cast<std::streamsize>(d.size() * 4));
+      npy::write_array<float>(os, d.data(), {idx.n, idx.dim});
     }
     B2_EXPECTS(bool(os), "Error writing %s", filename);
   });
@@ -1023,22 +1040,32 @@ cuvsError_t cuvsCagraDeserialize(cuvsResources_t res, const char* filename, cuvs
     std::ifstream is(filename, std::ios::in | std::ios::binary);
     B2_EXPECTS(bool(is), "Cannot open file %s", filename);
     char tag[4]{};
-    B2_EXPECTS(bool(is.read(tag, 4)), "Invalid or truncated index header in file %s", filename);
-    B2_EXPECTS(tag[0] == '<' && tag[1] == 'f' && tag[2] == '4', "Unsupported index dtype in %s", filename);
-    int64_t hdr[6];
-    is.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
-    B2_EXPECTS(bool(is) && hdr[0] == 1, "Unsupported cagra container version in %s", filename);
-    B2_EXPECTS(hdr[5] == 1, "index file %s was saved without the dataset; use cuvsCagraIndexFromArgs to attach one", filename);
+    B2_EXPECTS(bool(is.read(tag, 4)), "cagra::deserialize: failed to read dtype prefix");
+    B2_EXPECTS(tag[0] == '<' && tag[1] == 'f' && tag[2] == '4', "cagra::deserialize: serialized dtype prefix does not match requested type");
+    const int ver = npy::read_scalar<int32_t>(is, filename);
+    B2_EXPECTS(ver == 5, "serialization version mismatch, expected %d, got %d ", 5, ver);
     auto idx    = std::make_unique<cagra_index>();
     idx->device = r->device;
-    idx->metric = static_cast<cuvsDistanceType>(hdr[1]);
-    idx->n = hdr[2]; idx->dim = static_cast<int>(hdr[3]); idx->degree = static_cast<int>(hdr[4]);
-    idx->ld = (idx->dim + 3) & ~3;
+    idx->n      = npy::read_scalar<uint32_t>(is, filename);
+    idx->dim    = static_cast<int>(npy::read_scalar<uint32_t>(is, filename));
+    idx->degree = static_cast<int>(npy::read_scalar<uint32_t>(is, filename));
+    idx->metric = static_cast<cuvsDistanceType>(npy::read_scalar<int32_t>(is, filename));
+    idx->ld     = (idx->dim + 3) & ~3;
     std::vector<uint32_t> g(static_cast<size_t>(idx->n) * idx->degree);
-    is.read(reinterpret_cast<char*>(g.data()), static_cast<std::streamsize>(g.size() * 4));
+    npy::read_array<uint32_t>(is, g.data(), static_cast<int64_t>(g.size()), filename);
+    const uint32_t content_map = npy::read_scalar<uint32_t>(is, filename);
+    B2_EXPECTS(content_map & 1u, "index file %s was saved without the dataset; use cuvsCagraIndexFromArgs to attach one", filename);
+    const uint32_t inst = npy::read_scalar<uint32_t>(is, filename);
+    B2_EXPECTS(inst == 2u, "cagra::deserialize: dataset instance tag %u is not supported by this build (strided fp32 datasets only)", inst);
+    const uint32_t dt = npy::read_scalar<uint32_t>(is, filename);
+    B2_EXPECTS(dt == static_cast<uint32_t>(CUDA_R_32F), "Failed to deserialize dataset: unsupported strided dataset element type %u.", dt);
+    const int64_t rows = npy::read_scalar<int64_t>(is, filename);
+    const uint32_t dim = npy::read_scalar<uint32_t>(is, filename);
+    (void)npy::read_scalar<uint32_t>(is, filename);  // stride of the writer's device copy; rows are stored unpadded
+    B2_EXPECTS(rows == idx->n && static_cast<int>(dim) == idx->dim, "cagra::deserialize: dataset [%lld, %u] does not match the graph [%lld rows], dim %d",
+               (long long)rows, dim, (long long)idx->n, idx->dim);
     std::vector<float> d(static_cast<size_t>(idx->n) * idx->dim);
-    is.read(reinterpret_cast<char*>(d.data()), static_cast<std::streamsize>(d.size() * 4));
-    B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+    npy::read_array<float>(is, d.data(), static_cast<int64_t>(d.size()), filename);
     idx->graph_own.alloc(g.size());
     idx->data_own.alloc(static_cast<size_t>(idx->n) * idx->ld);
     B2_CUDA(cudaMemcpyAsync(idx->graph_own.data(), g.data(), g.size() * 4, cudaMemcpyHostToDevice, r->stream));

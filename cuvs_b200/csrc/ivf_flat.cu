@@ -18,6 +18,7 @@
 #include "exact.cuh"
 #include "ivf_common.cuh"
 #include "ivf_lists.cuh"
+#include "npy_io.hpp"
 #include "select_k.cuh"
 #include "timing.hpp"
 
@@ -562,7 +563,19 @@ cuvsError_t cuvsIvfFlatExtend(cuvsResources_t res, DLManagedTensor* new_vectors,
   });
 }
 
-// Own container: "<f4\0" tag, header scalars, centres, per-list sizes, then rows + ids list by list.
+// cuVS index file, serialization version 4 (cpp/src/neighbors/ivf_flat/ivf_flat_serialize.cuh:25-84; per-list records
+// cpp/src/neighbors/ivf_list.cuh:108-133): the 4-byte dtype tag "<f4\0", then NPY records (npy_io.hpp) —
+//   version i4 = 4, size i8, dim u4, n_lists u4, metric i4, adaptive_centers u1, conservative_memory_allocation u1,
+//   centers f4 [n_lists, dim], has_norms u1 (+ center_norms f4 [n_lists] for L2), list_sizes u4 [n_lists], then per list:
+//   capacity u4 = size rounded up to 32 and (capacity > 0) data f4 [capacity, dim] in the reference's interleaved layout
+//   (groups of 32 rows, element (r, k) at (r/32)*32*dim + (k/veclen)*32*veclen + (r%32)*veclen + k%veclen, veclen = 4 when
+//   dim % 4 == 0 else 1: ivf_flat.hpp:184-201) and indices i8 [capacity] (-1 = kInvalidRecord on the padding rows).
+namespace {
+
+inline int flat_veclen(int dim) { return dim % 4 == 0 ? 4 : 1; }
+
+}  // namespace
+
 cuvsError_t cuvsIvfFlatSerialize(cuvsResources_t res, const char* filename, cuvsIvfFlatIndex_t index)
 {
   return guarded([=] {
@@ -572,25 +585,49 @@ cuvsError_t cuvsIvfFlatSerialize(cuvsResources_t res, const char* filename, cuvs
     B2_EXPECTS(bool(os), "Cannot open file %s", filename);
     const char tag[4] = {'<', 'f', '4', 0};
     os.write(tag, 4);
-    int32_t hdr[4] = {1 /*version*/, int32_t(idx.metric), idx.dim, int32_t(idx.n_lists)};
-    os.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+    npy::write_scalar<int32_t>(os, 4);
+    npy::write_scalar<int64_t>(os, idx.lists.size);
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.dim));
+    npy::write_scalar<uint32_t>(os, idx.n_lists);
+    npy::write_scalar<int32_t>(os, static_cast<int32_t>(idx.metric));
+    npy::write_scalar<bool>(os, idx.adaptive_centers);
+    npy::write_scalar<bool>(os, false);
     std::vector<float> c(static_cast<size_t>(idx.n_lists) * idx.dim);
     B2_CUDA(cudaMemcpyAsync(c.data(), idx.centers.data(), c.size() * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
     B2_CUDA(cudaStreamSynchronize(r->stream));
-    os.write(reinterpret_cast<const char*>(c.data()), static_cast<std::streamsize>(c.size() * sizeof(float)));
-    os.write(reinterpret_cast<const char*>(idx.lists.h_sizes.data()), static_cast<std::streamsize>(sizeof(int64_t) * idx.n_lists));
-    std::vector<float> rows;
+    npy::write_array<float>(os, c.data(), {static_cast<int64_t>(idx.n_lists), idx.dim});
+    const bool has_norms = is_l2(idx.metric);
+    npy::write_scalar<bool>(os, has_norms);
+    if (has_norms) {
+      std::vector<float> cn(idx.n_lists);
+      for (uint32_t l = 0; l < idx.n_lists; ++l) {
+        float acc = 0.f;
+        for (int j = 0; j < idx.dim; ++j) acc = fmaf(c[static_cast<size_t>(l) * idx.dim + j], c[static_cast<size_t>(l) * idx.dim + j], acc);
+        cn[l] = acc;
+      }
+      npy::write_array<float>(os, cn.data(), {static_cast<int64_t>(idx.n_lists)});
+    }
+    std::vector<uint32_t> sizes(idx.n_lists);
+    for (uint32_t l = 0; l < idx.n_lists; ++l) sizes[l] = static_cast<uint32_t>(idx.lists.h_sizes[l]);
+    npy::write_array<uint32_t>(os, sizes.data(), {static_cast<int64_t>(idx.n_lists)});
+    std::vector<float> rows, inter;
     std::vector<int64_t> ids;
+    const int dim = idx.dim, vl = flat_veclen(dim);
     for (uint32_t l = 0; l < idx.n_lists; ++l) {
-      int64_t sz = idx.lists.h_sizes[l];
-      if (!sz) continue;
-      rows.resize(static_cast<size_t>(sz) * idx.dim);
-      ids.resize(static_cast<size_t>(sz));
-      B2_CUDA(cudaMemcpyAsync(rows.data(), idx.data.data() + idx.lists.h_offsets[l] * idx.dim, rows.size() * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
-      B2_CUDA(cudaMemcpyAsync(ids.data(), idx.ids.data() + idx.lists.h_offsets[l], ids.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, r->stream));
+      const int64_t sz = idx.lists.h_sizes[l], cap = (sz + 31) / 32 * 32;
+      npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(cap));
+      if (!cap) continue;
+      rows.resize(static_cast<size_t>(sz) * dim);
+      ids.assign(static_cast<size_t>(cap), int64_t(-1));
+      inter.assign(static_cast<size_t>(cap) * dim, 0.f);
+      B2_CUDA(cudaMemcpyAsync(rows.data(), idx.data.data() + idx.lists.h_offsets[l] * dim, rows.size() * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+      B2_CUDA(cudaMemcpyAsync(ids.data(), idx.ids.data() + idx.lists.h_offsets[l], static_cast<size_t>(sz) * sizeof(int64_t), cudaMemcpyDeviceToHost, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
-      os.write(reinterpret_cast<const char*>(rows.data()), static_cast<std::streamsize>(rows.size() * sizeof(float)));
-      os.write(reinterpret_cast<const char*>(ids.data()), static_cast<std::streamsize>(ids.size() * sizeof(int64_t)));
+      for (int64_t rr = 0; rr < sz; ++rr)
+        for (int k = 0; k < dim; ++k)
+          inter[static_cast<size_t>((rr / 32) * 32 * dim + (k / vl) * 32 * vl + (rr % 32) * vl + k % vl)] = rows[static_cast<size_t>(rr) * dim + k];
+      npy::write_array<float>(os, inter.data(), {cap, dim});
+      npy::write_array<int64_t>(os, ids.data(), {cap});
     }
     B2_EXPECTS(bool(os), "Error writing %s", filename);
   });
@@ -604,43 +641,58 @@ cuvsError_t cuvsIvfFlatDeserialize(cuvsResources_t res, const char* filename, cu
     std::ifstream is(filename, std::ios::in | std::ios::binary);
     B2_EXPECTS(bool(is), "Cannot open file %s", filename);
     char tag[4]{};
-    B2_EXPECTS(bool(is.read(tag, 4)), "Invalid or truncated index header in file %s", filename);
-    B2_EXPECTS(tag[0] == '<' && tag[1] == 'f' && tag[2] == '4', "Unsupported index dtype in %s", filename);
-    int32_t hdr[4];
-    is.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
-    B2_EXPECTS(bool(is) && hdr[0] == 1, "Unsupported ivf_flat container version in %s", filename);
+    B2_EXPECTS(bool(is.read(tag, 4)), "ivf_flat::deserialize: failed to read dtype prefix");
+    B2_EXPECTS(tag[0] == '<' && tag[1] == 'f' && tag[2] == '4', "ivf_flat::deserialize: serialized dtype prefix does not match requested type");
+    const int ver = npy::read_scalar<int32_t>(is, filename);
+    B2_EXPECTS(ver == 4, "serialization version mismatch, expected %d, got %d ", 4, ver);
+    const int64_t n_rows = npy::read_scalar<int64_t>(is, filename);
     auto idx      = std::make_unique<ivf_flat_index>();
     idx->device   = r->device;
-    idx->metric   = static_cast<cuvsDistanceType>(hdr[1]);
-    idx->dim      = hdr[2];
-    idx->n_lists  = static_cast<uint32_t>(hdr[3]);
+    idx->dim      = static_cast<int>(npy::read_scalar<uint32_t>(is, filename));
+    idx->n_lists  = npy::read_scalar<uint32_t>(is, filename);
+    idx->metric   = static_cast<cuvsDistanceType>(npy::read_scalar<int32_t>(is, filename));
+    idx->adaptive_centers = npy::read_scalar<uint8_t>(is, filename) != 0;
+    (void)npy::read_scalar<uint8_t>(is, filename);  // conservative_memory_allocation: an allocation policy, nothing to restore
     std::vector<float> c(static_cast<size_t>(idx->n_lists) * idx->dim);
-    is.read(reinterpret_cast<char*>(c.data()), static_cast<std::streamsize>(c.size() * sizeof(float)));
-    std::vector<int64_t> sizes(idx->n_lists);
-    is.read(reinterpret_cast<char*>(sizes.data()), static_cast<std::streamsize>(sizeof(int64_t) * idx->n_lists));
-    B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+    npy::read_array<float>(is, c.data(), static_cast<int64_t>(c.size()), filename);
+    if (npy::read_scalar<uint8_t>(is, filename) != 0) {
+      std::vector<float> cn(idx->n_lists);  // recomputed on load (refresh_centers_tc)
+      npy::read_array<float>(is, cn.data(), idx->n_lists, filename);
+    }
+    std::vector<uint32_t> sizes32(idx->n_lists);
+    npy::read_array<uint32_t>(is, sizes32.data(), idx->n_lists, filename);
+    std::vector<int64_t> sizes(sizes32.begin(), sizes32.end());
     idx->centers.alloc(c.size());
     B2_CUDA(cudaMemcpyAsync(idx->centers.data(), c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
     B2_CUDA(cudaStreamSynchronize(r->stream));
     refresh_centers_tc(r, *idx);
     idx->lists.set_sizes(r->stream, sizes);
+    B2_EXPECTS(idx->lists.size == n_rows, "ivf_flat::deserialize: list sizes sum to %lld, header says %lld rows", (long long)idx->lists.size,
+               (long long)n_rows);
     const int64_t R = idx->lists.rows_total;
     idx->data.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)) * idx->dim);
     idx->ids.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)));
     B2_CUDA(cudaMemsetAsync(idx->data.data(), 0, sizeof(float) * static_cast<size_t>(R) * idx->dim, r->stream));
     if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, kPadId);
-    std::vector<float> rows;
+    std::vector<float> rows, inter;
     std::vector<int64_t> ids;
+    const int dim = idx->dim, vl = flat_veclen(dim);
     for (uint32_t l = 0; l < idx->n_lists; ++l) {
-      int64_t sz = sizes[l];
+      const int64_t cap = npy::read_scalar<uint32_t>(is, filename);
+      const int64_t sz  = sizes[l];
+      B2_EXPECTS(cap >= sz, "ivf_flat::deserialize: list %u stores %lld rows, list_sizes says %lld", l, (long long)cap, (long long)sz);
+      if (!cap) continue;
+      inter.resize(static_cast<size_t>(cap) * dim);
+      ids.resize(static_cast<size_t>(cap));
+      npy::read_array<float>(is, inter.data(), cap * dim, filename);
+      npy::read_array<int64_t>(is, ids.data(), cap, filename);
       if (!sz) continue;
-      rows.resize(static_cast<size_t>(sz) * idx->dim);
-      ids.resize(static_cast<size_t>(sz));
-      is.read(reinterpret_cast<char*>(rows.data()), static_cast<std::streamsize>(rows.size() * sizeof(float)));
-      is.read(reinterpret_cast<char*>(ids.data()), static_cast<std::streamsize>(ids.size() * sizeof(int64_t)));
-      B2_EXPECTS(bool(is), "Truncated index file %s", filename);
-      B2_CUDA(cudaMemcpyAsync(idx->data.data() + idx->lists.h_offsets[l] * idx->dim, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
-      B2_CUDA(cudaMemcpyAsync(idx->ids.data() + idx->lists.h_offsets[l], ids.data(), ids.size() * sizeof(int64_t), cudaMemcpyHostToDevice, r->stream));
+      rows.resize(static_cast<size_t>(sz) * dim);
+      for (int64_t rr = 0; rr < sz; ++rr)
+        for (int k = 0; k < dim; ++k)
+          rows[static_cast<size_t>(rr) * dim + k] = inter[static_cast<size_t>((rr / 32) * 32 * dim + (k / vl) * 32 * vl + (rr % 32) * vl + k % vl)];
+      B2_CUDA(cudaMemcpyAsync(idx->data.data() + idx->lists.h_offsets[l] * dim, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+      B2_CUDA(cudaMemcpyAsync(idx->ids.data() + idx->lists.h_offsets[l], ids.data(), static_cast<size_t>(sz) * sizeof(int64_t), cudaMemcpyHostToDevice, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
     }
     refresh_tc_side(r, *idx);

@@ -27,6 +27,7 @@
 #include "exact.cuh"
 #include "ivf_common.cuh"
 #include "ivf_lists.cuh"
+#include "npy_io.hpp"
 #include "scan_pq.cuh"
 #include "select_k.cuh"
 #include "timing.hpp"
@@ -1224,7 +1225,65 @@ cuvsError_t cuvsIvfPqExtend(cuvsResources_t res, DLManagedTensor* new_vectors, D
   });
 }
 
-// Own container (version 1): header scalars, centres, rotation, codebooks, list sizes, then codes + ids list by list.
+// cuVS index file, serialization version 4 (cpp/src/neighbors/ivf_pq/ivf_pq_serialize.cuh:25-86; per-list records
+// cpp/src/neighbors/ivf_list.cuh:108-133): a sequence of NPY records (npy_io.hpp) —
+//   version i4 = 4, size i8, dim u4, pq_bits u4, pq_dim u4, conservative_memory_allocation u1, metric i4, codebook_kind i4,
+//   codes_layout i4, n_lists u4, pq_centers f4 [pq_dim | n_lists, pq_len, 2^pq_bits], centers f4 [n_lists, dim_ext],
+//   centers_rot f4 [n_lists, rot_dim], rotation_matrix f4 [rot_dim, dim], list_sizes u4 [n_lists], then per list:
+//   size u4 and (size > 0) codes u1 in the reference's list layout — INTERLEAVED [ceil(size/32), ceil(pq_dim/C), 32, 16]
+//   with C = 128/pq_bits codes per 16-byte chunk (ivf_pq.hpp:235-296, bit order ivf_pq_codepacking.cuh:28-78), or FLAT
+//   [size, ceil(pq_dim*pq_bits/8)] — and indices i8 [size].
+// A cuVS build loads these files with ivf_pq::deserialize and this library loads files written by cuVS.
+namespace {
+
+// [n, pq_dim] one code per byte -> interleaved groups of 32 (host)
+std::vector<uint8_t> pack_interleaved(const uint8_t* flat, int64_t n, int pq_dim, int pq_bits)
+{
+  const int C = 128 / pq_bits, n_chunks = (pq_dim + C - 1) / C;
+  std::vector<uint8_t> out(static_cast<size_t>((n + 31) / 32) * n_chunks * 32 * 16, 0);
+  for (int64_t v = 0; v < n; ++v) {
+    const int64_t g = v / 32, l = v % 32;
+    for (int j = 0; j < pq_dim; ++j) {
+      const int bit = (j % C) * pq_bits;
+      uint8_t* chunk = out.data() + ((g * n_chunks + j / C) * 32 + l) * 16;
+      const uint32_t val = static_cast<uint32_t>(flat[v * pq_dim + j]) << (bit % 8);
+      chunk[bit / 8] |= static_cast<uint8_t>(val & 0xffu);
+      if (val >> 8) chunk[bit / 8 + 1] |= static_cast<uint8_t>(val >> 8);
+    }
+  }
+  return out;
+}
+void unpack_interleaved(const uint8_t* packed, int64_t n, int pq_dim, int pq_bits, uint8_t* flat)
+{
+  const int C = 128 / pq_bits, n_chunks = (pq_dim + C - 1) / C;
+  const uint32_t mask = (1u << pq_bits) - 1u;
+  for (int64_t v = 0; v < n; ++v) {
+    const int64_t g = v / 32, l = v % 32;
+    for (int j = 0; j < pq_dim; ++j) {
+      const int bit = (j % C) * pq_bits, byte = bit / 8;
+      const uint8_t* chunk = packed + ((g * n_chunks + j / C) * 32 + l) * 16;
+      uint32_t word = chunk[byte];
+      if (byte + 1 < 16) word |= static_cast<uint32_t>(chunk[byte + 1]) << 8;
+      flat[v * pq_dim + j] = static_cast<uint8_t>((word >> (bit % 8)) & mask);
+    }
+  }
+}
+// FLAT layout: every vector's codes bit-packed contiguously, ceil(pq_dim * pq_bits / 8) bytes per row
+void unpack_flat_rows(const uint8_t* packed, int64_t n, int pq_dim, int pq_bits, uint8_t* flat)
+{
+  const int ld = (pq_dim * pq_bits + 7) / 8;
+  const uint32_t mask = (1u << pq_bits) - 1u;
+  for (int64_t v = 0; v < n; ++v)
+    for (int j = 0; j < pq_dim; ++j) {
+      const int bit = j * pq_bits, byte = bit / 8;
+      uint32_t word = packed[v * ld + byte];
+      if (byte + 1 < ld) word |= static_cast<uint32_t>(packed[v * ld + byte + 1]) << 8;
+      flat[v * pq_dim + j] = static_cast<uint8_t>((word >> (bit % 8)) & mask);
+    }
+}
+
+}  // namespace
+
 cuvsError_t cuvsIvfPqSerialize(cuvsResources_t res, const char* filename, cuvsIvfPqIndex_t index)
 {
   return guarded([=] {
@@ -1232,33 +1291,47 @@ cuvsError_t cuvsIvfPqSerialize(cuvsResources_t res, const char* filename, cuvsIv
     auto& idx = pq_of(index);
     std::ofstream os(filename, std::ios::out | std::ios::binary);
     B2_EXPECTS(bool(os), "Cannot open file %s", filename);
-    int32_t hdr[10] = {0x42325051 /*"B2PQ"*/, 1, int32_t(idx.metric), idx.dim, int32_t(idx.n_lists), idx.pq_dim, idx.pq_bits,
-                       idx.codebook_kind, idx.conservative ? 1 : 0, idx.rot_dim};
-    os.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
-    auto dump = [&](const float* p, size_t n) {
+    npy::write_scalar<int32_t>(os, 4);
+    npy::write_scalar<int64_t>(os, idx.lists.size);
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.dim));
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.pq_bits));
+    npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(idx.pq_dim));
+    npy::write_scalar<bool>(os, idx.conservative);
+    npy::write_scalar<int32_t>(os, static_cast<int32_t>(idx.metric));
+    npy::write_scalar<int32_t>(os, static_cast<int32_t>(idx.codebook_kind));
+    npy::write_scalar<int32_t>(os, static_cast<int32_t>(CUVS_IVF_PQ_LIST_LAYOUT_INTERLEAVED));
+    npy::write_scalar<uint32_t>(os, idx.n_lists);
+    auto dump = [&](const float* p, std::vector<int64_t> shape) {
+      size_t n = 1;
+      for (auto e : shape) n *= static_cast<size_t>(e);
       std::vector<float> h(n);
       B2_CUDA(cudaMemcpyAsync(h.data(), p, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
-      os.write(reinterpret_cast<const char*>(h.data()), static_cast<std::streamsize>(n * sizeof(float)));
+      npy::write_array<float>(os, h.data(), shape);
     };
     const int64_t nb = idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_CLUSTER ? idx.n_lists : idx.pq_dim;
-    dump(idx.centers.data(), static_cast<size_t>(idx.n_lists) * idx.dim);
-    dump(idx.centers_rot.data(), static_cast<size_t>(idx.n_lists) * idx.rot_dim);
-    dump(idx.rotation.data(), static_cast<size_t>(idx.rot_dim) * idx.dim);
-    dump(idx.pq_centers.data(), static_cast<size_t>(nb) * idx.pq_len * idx.book());
-    os.write(reinterpret_cast<const char*>(idx.lists.h_sizes.data()), static_cast<std::streamsize>(sizeof(int64_t) * idx.n_lists));
+    dump(idx.pq_centers.data(), {nb, idx.pq_len, idx.book()});
+    dump(idx.centers_ext.data(), {static_cast<int64_t>(idx.n_lists), idx.dim_ext});
+    dump(idx.centers_rot.data(), {static_cast<int64_t>(idx.n_lists), idx.rot_dim});
+    dump(idx.rotation.data(), {idx.rot_dim, idx.dim});
+    std::vector<uint32_t> sizes(idx.n_lists);
+    for (uint32_t l = 0; l < idx.n_lists; ++l) sizes[l] = static_cast<uint32_t>(idx.lists.h_sizes[l]);
+    npy::write_array<uint32_t>(os, sizes.data(), {static_cast<int64_t>(idx.n_lists)});
     std::vector<uint8_t> codes;
     std::vector<int64_t> ids;
+    const int C = 128 / idx.pq_bits;
     for (uint32_t l = 0; l < idx.n_lists; ++l) {
-      int64_t sz = idx.lists.h_sizes[l];
+      const int64_t sz = idx.lists.h_sizes[l];
+      npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(sz));
       if (!sz) continue;
       codes.resize(static_cast<size_t>(sz) * idx.pq_dim);
       ids.resize(static_cast<size_t>(sz));
       B2_CUDA(cudaMemcpyAsync(codes.data(), idx.codes.data() + idx.lists.h_offsets[l] * idx.pq_dim, codes.size(), cudaMemcpyDeviceToHost, r->stream));
       B2_CUDA(cudaMemcpyAsync(ids.data(), idx.ids.data() + idx.lists.h_offsets[l], ids.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
-      os.write(reinterpret_cast<const char*>(codes.data()), static_cast<std::streamsize>(codes.size()));
-      os.write(reinterpret_cast<const char*>(ids.data()), static_cast<std::streamsize>(ids.size() * sizeof(int64_t)));
+      const std::vector<uint8_t> packed = pack_interleaved(codes.data(), sz, idx.pq_dim, idx.pq_bits);
+      npy::write_array<uint8_t>(os, packed.data(), {(sz + 31) / 32, (idx.pq_dim + C - 1) / C, 32, 16});
+      npy::write_array<int64_t>(os, ids.data(), {sz});
     }
     B2_EXPECTS(bool(os), "Error writing %s", filename);
   });
@@ -1271,49 +1344,75 @@ cuvsError_t cuvsIvfPqDeserialize(cuvsResources_t res, const char* filename, cuvs
     B2_EXPECTS(index && filename, "null argument");
     std::ifstream is(filename, std::ios::in | std::ios::binary);
     B2_EXPECTS(bool(is), "Cannot open file %s", filename);
-    int32_t hdr[10];
-    is.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
-    B2_EXPECTS(bool(is) && hdr[0] == 0x42325051 && hdr[1] == 1, "Unsupported ivf_pq container in %s", filename);
+    const int ver = npy::read_scalar<int32_t>(is, filename);
+    B2_EXPECTS(ver == 4, "serialization version mismatch %d vs. %d", ver, 4);
+    const int64_t n_rows  = npy::read_scalar<int64_t>(is, filename);
+    const uint32_t dim    = npy::read_scalar<uint32_t>(is, filename);
+    const uint32_t pqbits = npy::read_scalar<uint32_t>(is, filename);
+    const uint32_t pqdim  = npy::read_scalar<uint32_t>(is, filename);
+    const bool cma        = npy::read_scalar<uint8_t>(is, filename) != 0;
+    const int32_t metric  = npy::read_scalar<int32_t>(is, filename);
+    const int32_t cb_kind = npy::read_scalar<int32_t>(is, filename);
+    const int32_t layout  = npy::read_scalar<int32_t>(is, filename);
+    const uint32_t nlists = npy::read_scalar<uint32_t>(is, filename);
+    B2_EXPECTS(cb_kind == 0 || cb_kind == 1, "ivf_pq::deserialize: invalid codebook_gen value %d", cb_kind);
+    B2_EXPECTS(layout == 0 || layout == 1, "ivf_pq::deserialize: invalid list_layout value %d", layout);
     auto idx    = std::make_unique<ivf_pq_index>();
     idx->device = r->device;
-    cuvsIvfPqIndexParams p{static_cast<cuvsDistanceType>(hdr[2]), 2.0f, true, static_cast<uint32_t>(hdr[4]), 20, 0.5,
-                           static_cast<uint32_t>(hdr[6]), static_cast<uint32_t>(hdr[5]), static_cast<cuvsIvfPqCodebookGen>(hdr[7]),
-                           false, hdr[8] != 0, 256, CUVS_IVF_PQ_LIST_LAYOUT_INTERLEAVED};
-    init_shape(*idx, p, hdr[3]);
-    B2_EXPECTS(idx->rot_dim == hdr[9], "corrupt header in %s", filename);
+    cuvsIvfPqIndexParams p{static_cast<cuvsDistanceType>(metric), 2.0f, true, nlists, 20, 0.5, pqbits, pqdim,
+                           static_cast<cuvsIvfPqCodebookGen>(cb_kind), false, cma, 256, CUVS_IVF_PQ_LIST_LAYOUT_INTERLEAVED};
+    init_shape(*idx, p, static_cast<int>(dim));
     auto load = [&](owned<float>& dst, size_t n) {
       std::vector<float> h(n);
-      is.read(reinterpret_cast<char*>(h.data()), static_cast<std::streamsize>(n * sizeof(float)));
-      B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+      npy::read_array<float>(is, h.data(), static_cast<int64_t>(n), filename);
       dst.alloc(n);
       B2_CUDA(cudaMemcpyAsync(dst.data(), h.data(), n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
+      return h;
     };
     const int64_t nb = idx->codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_CLUSTER ? idx->n_lists : idx->pq_dim;
-    load(idx->centers, static_cast<size_t>(idx->n_lists) * idx->dim);
+    load(idx->pq_centers, static_cast<size_t>(nb) * idx->pq_len * idx->book());
+    {
+      // centers are stored padded: [n_lists, dim_ext] with |c|^2 in column dim (ivf_pq_index.cu:78-80)
+      std::vector<float> ext = load(idx->centers_ext, static_cast<size_t>(idx->n_lists) * idx->dim_ext);
+      std::vector<float> c(static_cast<size_t>(idx->n_lists) * idx->dim);
+      for (uint32_t l = 0; l < idx->n_lists; ++l)
+        std::copy(ext.begin() + static_cast<size_t>(l) * idx->dim_ext, ext.begin() + static_cast<size_t>(l) * idx->dim_ext + idx->dim,
+                  c.begin() + static_cast<size_t>(l) * idx->dim);
+      idx->centers.alloc(c.size());
+      B2_CUDA(cudaMemcpyAsync(idx->centers.data(), c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+      B2_CUDA(cudaStreamSynchronize(r->stream));
+    }
     load(idx->centers_rot, static_cast<size_t>(idx->n_lists) * idx->rot_dim);
     load(idx->rotation, static_cast<size_t>(idx->rot_dim) * idx->dim);
-    load(idx->pq_centers, static_cast<size_t>(nb) * idx->pq_len * idx->book());
     refresh_centers(r, *idx);
-    std::vector<int64_t> sizes(idx->n_lists);
-    is.read(reinterpret_cast<char*>(sizes.data()), static_cast<std::streamsize>(sizeof(int64_t) * idx->n_lists));
-    B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+    std::vector<uint32_t> sizes32(idx->n_lists);
+    npy::read_array<uint32_t>(is, sizes32.data(), idx->n_lists, filename);
+    std::vector<int64_t> sizes(sizes32.begin(), sizes32.end());
     idx->lists.set_sizes(r->stream, sizes);
+    B2_EXPECTS(idx->lists.size == n_rows, "ivf_pq::deserialize: list sizes sum to %lld, header says %lld rows", (long long)idx->lists.size,
+               (long long)n_rows);
     const int64_t R = idx->lists.rows_total;
     idx->codes.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)) * idx->pq_dim);
     idx->ids.alloc(static_cast<size_t>(std::max<int64_t>(R, 1)));
     B2_CUDA(cudaMemsetAsync(idx->codes.data(), 0, static_cast<size_t>(R) * idx->pq_dim, r->stream));
     if (R) fill_i64_kernel<<<blocks_for(R, 256), 256, 0, r->stream>>>(idx->ids.data(), R, kPadId);
-    std::vector<uint8_t> codes;
+    std::vector<uint8_t> packed, codes;
     std::vector<int64_t> ids;
+    const int C = 128 / idx->pq_bits;
     for (uint32_t l = 0; l < idx->n_lists; ++l) {
-      int64_t sz = sizes[l];
+      const int64_t sz = npy::read_scalar<uint32_t>(is, filename);
+      B2_EXPECTS(sz == sizes[l], "ivf_pq::deserialize: list %u holds %lld rows, list_sizes says %lld", l, (long long)sz, (long long)sizes[l]);
       if (!sz) continue;
+      const int64_t pbytes = layout == 1 ? (sz + 31) / 32 * ((idx->pq_dim + C - 1) / C) * 32 * 16
+                                         : sz * ((idx->pq_dim * idx->pq_bits + 7) / 8);
+      packed.resize(static_cast<size_t>(pbytes));
       codes.resize(static_cast<size_t>(sz) * idx->pq_dim);
       ids.resize(static_cast<size_t>(sz));
-      is.read(reinterpret_cast<char*>(codes.data()), static_cast<std::streamsize>(codes.size()));
-      is.read(reinterpret_cast<char*>(ids.data()), static_cast<std::streamsize>(ids.size() * sizeof(int64_t)));
-      B2_EXPECTS(bool(is), "Truncated index file %s", filename);
+      npy::read_array<uint8_t>(is, packed.data(), pbytes, filename);
+      npy::read_array<int64_t>(is, ids.data(), sz, filename);
+      if (layout == 1) unpack_interleaved(packed.data(), sz, idx->pq_dim, idx->pq_bits, codes.data());
+      else unpack_flat_rows(packed.data(), sz, idx->pq_dim, idx->pq_bits, codes.data());
       B2_CUDA(cudaMemcpyAsync(idx->codes.data() + idx->lists.h_offsets[l] * idx->pq_dim, codes.data(), codes.size(), cudaMemcpyHostToDevice, r->stream));
       B2_CUDA(cudaMemcpyAsync(idx->ids.data() + idx->lists.h_offsets[l], ids.data(), ids.size() * sizeof(int64_t), cudaMemcpyHostToDevice, r->stream));
       B2_CUDA(cudaStreamSynchronize(r->stream));
