@@ -160,6 +160,12 @@ struct cagra_launch {
   const uint32_t* keep_bits;  // bitset pre-filter over node ids (bit = 1 keeps), null = none
   int64_t n_bits;
   unsigned long long* work_counter;  // next query index (persistent warps)
+  // multi-walker mode (the reference's MULTI_CTA algorithm, search_multi_cta_jit.cuh:56-363): `walkers` warps per query,
+  // each with its own 32-entry list and search_width 1, sharing ONE table of traversed parents per query
+  int walkers;                  // 0 = single-walker kernel
+  uint32_t* traversed;          // [nq << traversed_bitlen], initialised to kInvalid by the host
+  uint32_t traversed_bitlen;
+  unsigned long long* mc_keys;  // [nq, walkers, 32] every walker's final sorted list (dist_key << 32 | id)
 };
 
 // squared L2 / negative dot between the smem query and a dataset row, computed by a team of 8 lanes
@@ -237,9 +243,10 @@ __device__ __forceinline__ float walk_distance(const __half* data16, int ld16, c
 // EI = itopk / 32, EC = (search_width * degree rounded up to 32) / 32 ; buffer = EI + EC keys per lane
 constexpr int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int EI, int EC>
+template <int EI, int EC, bool MULTI = false>
 __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_search_kernel(cagra_launch p)
 {
+  static_assert(!MULTI || EI == 1, "a multi-walker list is 32 entries (search_multi_cta.cuh:119-127)");
   constexpr int EB = next_pow2(EI + EC);  // the bitonic network needs a power-of-two key count; spare keys stay ~0 (sort last)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -262,6 +269,11 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
   int64_t qi = 0;
   if (lane == 0) qi = static_cast<int64_t>(atomicAdd(p.work_counter, 1ull));
   qi = __shfl_sync(0xffffffffu, qi, 0);
+  int widx = 0;  // which of the query's walkers this warp is
+  if constexpr (MULTI) {
+    widx = static_cast<int>(qi % p.walkers);
+    qi /= p.walkers;
+  }
   if (qi >= p.nq) break;
 
   const uint32_t bitlen = p.small_hash_bitlen ? p.small_hash_bitlen : p.hash_bitlen;
@@ -287,7 +299,10 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
       for (int j = 0; j < p.num_random_samplings; ++j) {
         uint32_t seed = 0;
         if (valid_i) {
-          const uint64_t gid = static_cast<uint64_t>(i) + static_cast<uint64_t>(buf) * static_cast<uint64_t>(j);
+          // multi-walker: walker w draws the seeds a (w-th) CTA of the reference would (device_common_jit.cuh:65-74:
+          // gid = block_id + num_blocks * (i + num_pickup * j))
+          const uint64_t gid = MULTI ? static_cast<uint64_t>(widx) + static_cast<uint64_t>(p.walkers) * (static_cast<uint64_t>(i) + static_cast<uint64_t>(buf) * static_cast<uint64_t>(j))
+                                     : static_cast<uint64_t>(i) + static_cast<uint64_t>(buf) * static_cast<uint64_t>(j);
           seed               = static_cast<uint32_t>(xorshift64(gid ^ p.rand_xor_mask) % static_cast<uint64_t>(p.n));
         }
         const float dd = walk_distance(p.data16, p.ld16, p.data, p.ld, p.dim, seed, sq, t, ip);
@@ -330,6 +345,17 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const uint32_t pid = __shfl_sync(0xffffffffu, id, src);
+        if constexpr (MULTI) {
+          // a node is expanded by exactly ONE walker of the query: the shared traversed table decides
+          // (search_multi_cta_device_helpers.cuh pickup_next_parent: insert into traversed_hashmap, skip when present)
+          uint32_t fresh = 0;
+          if (lane == 0) fresh = hash_insert(p.traversed + (static_cast<size_t>(qi) << p.traversed_bitlen), p.traversed_bitlen, pid);
+          fresh = __shfl_sync(0xffffffffu, fresh, 0);
+          if (!fresh) {
+            if (lane == src) key[e] |= kMsb;  // somebody else's parent: never pick it again
+            continue;
+          }
+        }
         // mark as used; a node the filter rejects may serve as a stepping stone ONCE and then leaves the list
         // (search_single_cta_jit.cuh:297-316: filtered parents are invalidated after their children were expanded)
         if (lane == src) key[e] = (p.keep_bits != nullptr && !node_kept(p.keep_bits, p.n_bits, pid)) ? ~0ull : (key[e] | kMsb);
@@ -409,6 +435,12 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
     for (int e = 1; e < EB; ++e) key[e] = ~0ull;  // only the re-ranked 32 can be returned (k <= 32 in this mode)
     warp_bitonic_sort<EB>(key, lane);
   }
+  if constexpr (MULTI) {
+    // every walker hands its sorted 32-entry list to the per-query merge (cagra_merge_walkers_kernel)
+    p.mc_keys[(static_cast<size_t>(qi) * p.walkers + widx) * 32 + lane] = key[0] == ~0ull ? ~0ull : (key[0] & ~static_cast<uint64_t>(kMsb));
+    __syncwarp();
+    continue;
+  }
   // ---- results: first k entries of the sorted list
 #pragma unroll
   for (int e = 0; e < EI; ++e) {
@@ -426,6 +458,51 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
   if (p.out_iters && lane == 0) p.out_iters[qi] = iter + 1;
   __syncwarp();
   }  // next query
+}
+
+// Multi-walker epilogue: one warp per query merges its walkers' lists — sort, drop the ids several walkers found (their
+// keys are bit-identical: same id, same distance arithmetic), drop filtered nodes, emit the k best
+// (search_multi_cta.cuh:245-262: topk over num_cta_per_query * 32 intermediate results).
+template <int E>
+__global__ void __launch_bounds__(128) cagra_merge_walkers_kernel(const unsigned long long* __restrict__ keys, int64_t nq, int walkers, int k,
+                                                                   bool ip, const uint32_t* __restrict__ keep_bits, int64_t n_bits,
+                                                                   uint32_t* __restrict__ out32, int64_t* __restrict__ out64,
+                                                                   float* __restrict__ out_dist)
+{
+  const int lane   = threadIdx.x & 31;
+  const int64_t qi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (qi >= nq) return;
+  uint64_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    key[e] = e < walkers ? keys[(static_cast<size_t>(qi) * walkers + e) * 32 + lane] : ~0ull;
+    if (keep_bits != nullptr && key[e] != ~0ull && !node_kept(keep_bits, n_bits, static_cast<uint32_t>(key[e]))) key[e] = ~0ull;
+  }
+  warp_bitonic_sort<E>(key, lane);
+  uint64_t prev[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {  // striped order: element e*32 + lane; its predecessor sits in lane - 1 (or lane 31 of e - 1)
+    prev[e] = __shfl_up_sync(0xffffffffu, key[e], 1);
+    const uint64_t carry = __shfl_sync(0xffffffffu, key[e > 0 ? e - 1 : 0], 31);
+    if (lane == 0) prev[e] = e > 0 ? carry : ~key[e];
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (key[e] == prev[e]) key[e] = ~0ull;
+  warp_bitonic_sort<E>(key, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int r = e * 32 + lane;
+    if (r < k) {
+      const bool valid  = key[e] != ~0ull;
+      const uint32_t id = valid ? static_cast<uint32_t>(key[e]) : kInvalid;
+      float d           = valid ? key_dist(static_cast<uint32_t>(key[e] >> 32)) : FLT_MAX;
+      if (valid && ip) d = -d;
+      if (out32) out32[qi * k + r] = id;
+      if (out64) out64[qi * k + r] = valid ? static_cast<int64_t>(id) : -1;
+      out_dist[qi * k + r] = d;
+    }
+  }
 }
 
 struct cagra_plan {
@@ -476,10 +553,10 @@ cagra_plan make_plan(const cuvsCagraSearchParams& sp, int64_t n, int degree, int
   return pl;
 }
 
-template <int EI, int EC>
+template <int EI, int EC, bool MULTI = false>
 void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
 {
-  auto kern = cagra_search_kernel<EI, EC>;
+  auto kern = cagra_search_kernel<EI, EC, MULTI>;
   int warps = 16;
   while (warps > 1 && per_warp_smem * warps > 200 * 1024) warps >>= 1;
   const size_t smem = per_warp_smem * warps;
@@ -489,7 +566,13 @@ void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
   B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const unsigned grid = std::min<unsigned>(blocks_for(p.nq, warps), static_cast<unsigned>(std::max(per_sm, 1) * sms));
+  const int64_t n_walks = p.nq * (MULTI ? p.walkers : 1);
+  if (MULTI) {
+    // few walks: spread them over the SMs (one warp per CTA while the batch is smaller than the machine) instead of packing
+    // 16 of them into one CTA — the case the reference switches to multi-CTA for (search_plan.cuh:122-131)
+    while (warps > 1 && n_walks < static_cast<int64_t>(warps) * sms) warps >>= 1;
+  }
+  const unsigned grid = std::min<unsigned>(blocks_for(n_walks, warps), static_cast<unsigned>(std::max(per_sm, 1) * sms));
   dbuf<unsigned long long> counter(1, s);
   B2_CUDA(cudaMemsetAsync(counter.data(), 0, sizeof(unsigned long long), s));
   cagra_launch pl = p;
@@ -500,6 +583,73 @@ void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
   B2_CUDA(cudaGetLastError());
 }
 
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v)
+{
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// MULTI_CTA (search_multi_cta.cuh:100-262, plan search_plan.cuh:254-290): num_cta_per_query = max(search_width,
+// ceil(itopk / 32)) walkers per query, each a 32-entry list with search_width 1 and its own small visited hash; parents are
+// claimed through one traversed table per query; the walkers' lists are merged into the top-k.
+void cagra_search_multi(resources* res, const cagra_index& idx, const cuvsCagraSearchParams& sp, const float* queries, int64_t nq, int k,
+                        uint32_t* out32, int64_t* out64, float* out_dist, const uint32_t* keep_bits, int64_t n_bits)
+{
+  auto s = res->stream;
+  size_t itopk = sp.itopk_size ? sp.itopk_size : 64;
+  if (itopk % 32) itopk += 32 - itopk % 32;
+  const int walkers = static_cast<int>(std::max<size_t>(std::max<size_t>(sp.search_width, 1), itopk / 32));
+  B2_EXPECTS(walkers <= 16, "cagra multi-cta search: itopk_size / 32 = %d walkers per query exceeds the 16 this build merges", walkers);
+  B2_EXPECTS(walkers * 32 >= k, "`num_cta_per_query` (%d) * 32 must be equal to or greater than `topk` (%d)", walkers, k);
+  cuvsCagraSearchParams one = sp;  // the per-walker plan: itopk 32, search_width 1
+  one.itopk_size   = 32;
+  one.search_width = 1;
+  one.hashmap_mode = AUTO_HASH;
+  const cagra_plan pl = make_plan(one, idx.n, idx.degree, std::min(k, 32));
+  B2_EXPECTS(pl.small_hash_bitlen != 0, "cagra multi-cta search: graph_degree %d needs a visited table beyond the small-hash limit", idx.degree);
+  const int EC = (idx.degree + 31) / 32;
+  cagra_launch p{};
+  p.data = idx.data; p.graph = idx.graph; p.n = idx.n; p.dim = idx.dim; p.ld = idx.ld; p.degree = idx.degree;
+  p.data16 = nullptr; p.ld16 = 0;
+  p.queries = queries; p.nq = nq; p.metric = idx.metric == InnerProduct ? InnerProduct : L2Expanded;
+  p.k = k; p.itopk = 32; p.search_width = 1; p.min_iter = pl.min_iter; p.max_iter = pl.max_iter;
+  p.hash_bitlen = pl.hash_bitlen; p.small_hash_bitlen = pl.small_hash_bitlen; p.reset_interval = pl.reset_interval;
+  p.num_random_samplings = static_cast<int>(std::max<uint32_t>(sp.num_random_samplings, 1));
+  p.rand_xor_mask = sp.rand_xor_mask;
+  p.keep_bits = keep_bits; p.n_bits = n_bits;
+  p.walkers = walkers;
+  // traversed table: every walker claims at most max(32, max_iter) parents (search_plan.cuh:277-290)
+  const float fill = sp.hashmap_max_fill_rate > 0.f ? sp.hashmap_max_fill_rate : 0.5f;
+  uint32_t tb = std::max<uint32_t>(11, static_cast<uint32_t>(sp.hashmap_min_bitlen));
+  while (static_cast<size_t>(walkers) * std::max(32, pl.max_iter) > (size_t(1) << tb) * fill) ++tb;
+  B2_EXPECTS(tb <= 20, "hash_bitlen cannot be largen than 20 (1M). You can decrease itopk_size, search_width or max_iterations to reduce the required hashmap size.");
+  p.traversed_bitlen = tb;
+  dbuf<uint32_t> trav(static_cast<size_t>(nq) << tb, s);
+  dbuf<unsigned long long> keys(static_cast<size_t>(nq) * walkers * 32, s);
+  p.traversed = trav.data();
+  p.mc_keys   = keys.data();
+  count_launch();
+  fill_u32_kernel<<<blocks_for(static_cast<int64_t>(trav.size()), 256), 256, 0, s>>>(trav.data(), trav.size(), kInvalid);
+  const int qpad = (idx.dim + 3) & ~3;
+  int ebp = 1;
+  while (ebp < 1 + EC) ebp <<= 1;
+  const size_t per_warp = static_cast<size_t>(qpad) * 4 + (size_t(4) << pl.small_hash_bitlen) + static_cast<size_t>(ebp) * 32 * 8 + 16;
+  if (EC == 1) launch_search<1, 1, true>(s, p, per_warp);
+  else if (EC == 2) launch_search<1, 2, true>(s, p, per_warp);
+  else if (EC <= 4) launch_search<1, 4, true>(s, p, per_warp);
+  else B2_FAIL("cagra multi-cta search: graph_degree %d > 128 is not built", idx.degree);
+  const bool ip = idx.metric == InnerProduct;
+  count_launch();
+  const unsigned mgrid = blocks_for(nq * 32, 128);
+  if (walkers <= 1) cagra_merge_walkers_kernel<1><<<mgrid, 128, 0, s>>>(keys.data(), nq, walkers, k, ip, keep_bits, n_bits, out32, out64, out_dist);
+  else if (walkers <= 2) cagra_merge_walkers_kernel<2><<<mgrid, 128, 0, s>>>(keys.data(), nq, walkers, k, ip, keep_bits, n_bits, out32, out64, out_dist);
+  else if (walkers <= 4) cagra_merge_walkers_kernel<4><<<mgrid, 128, 0, s>>>(keys.data(), nq, walkers, k, ip, keep_bits, n_bits, out32, out64, out_dist);
+  else if (walkers <= 8) cagra_merge_walkers_kernel<8><<<mgrid, 128, 0, s>>>(keys.data(), nq, walkers, k, ip, keep_bits, n_bits, out32, out64, out_dist);
+  else cagra_merge_walkers_kernel<16><<<mgrid, 128, 0, s>>>(keys.data(), nq, walkers, k, ip, keep_bits, n_bits, out32, out64, out_dist);
+  B2_CUDA(cudaGetLastError());
+  if (idx.metric == L2SqrtExpanded) postprocess_distances(s, out_dist, nq * k, L2SqrtExpanded);
+}
+
 void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchParams& sp, const float* queries, int64_t nq, int k,
                   uint32_t* out32, int64_t* out64, float* out_dist, const uint32_t* keep_bits = nullptr, int64_t n_bits = 0)
 {
@@ -507,10 +657,19 @@ void cagra_search(resources* res, const cagra_index& idx, const cuvsCagraSearchP
   if (nq == 0) return;
   B2_EXPECTS(idx.metric == L2Expanded || idx.metric == InnerProduct || idx.metric == L2SqrtExpanded,
              "cagra search: unsupported metric %d", int(idx.metric));
+  B2_EXPECTS(!sp.persistent, "cagra search: the persistent (latency) mode is out of scope of this library");
+  // algo selection (search_plan.cuh:122-131): AUTO -> single-CTA when itopk <= 512 and the batch has at least 2 queries per
+  // SM, multi-CTA otherwise (small batches: several walkers per query keep the machine busy).  MULTI_KERNEL is served by the
+  // multi-walker kernel too.
+  int algo = static_cast<int>(sp.algo);
+  if (algo == AUTO) {
+    const size_t itopk_req = sp.itopk_size ? sp.itopk_size : 64;
+    algo = (itopk_req <= 512 && static_cast<size_t>(nq) >= static_cast<size_t>(sm_count_of(res->device)) * 2) ? SINGLE_CTA : MULTI_CTA;
+  }
+  if (algo != SINGLE_CTA) return cagra_search_multi(res, idx, sp, queries, nq, k, out32, out64, out_dist, keep_bits, n_bits);
   const cagra_plan pl = make_plan(sp, idx.n, idx.degree, k);
   const int w         = static_cast<int>(std::max<size_t>(sp.search_width, 1));
   B2_EXPECTS(w <= 4, "cagra search: search_width > 4 is not supported by this build (got %d)", w);
-  B2_EXPECTS(!sp.persistent, "cagra search: the persistent (latency) mode is out of scope of this library");
   const int n_cand = w * idx.degree;
   const int EI = pl.itopk / 32, EC = (n_cand + 31) / 32;
   cagra_launch p{};

@@ -52,7 +52,8 @@ def test_walk_matches_oracle(n, d, degree, itopk, width, k):
     l0 = launches()
     index = m.from_graph(torch.from_numpy(g.astype(np.int64)).cuda(), torch.from_numpy(ds).cuda())
     assert (len(index), index.dim, index.graph_degree) == (n, d, degree)
-    dist, idx = m.search(m.SearchParams(itopk_size=itopk, search_width=width), index, torch.from_numpy(qs).cuda(), k)
+    # (algo pinned: a 200-query batch is below 2 queries per SM, where AUTO picks the multi-CTA walk, search_plan.cuh:122-131)
+    dist, idx = m.search(m.SearchParams(itopk_size=itopk, search_width=width, algo="single_cta"), index, torch.from_numpy(qs).cuda(), k)
     assert launches() > l0
     dist, idx = dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
     rd, ri, _ = oracle.cagra_search(g, ds, qs, k, itopk=itopk, search_width=width)
@@ -146,7 +147,7 @@ def test_fp16_walk_reranks_with_fp32_rows():
     ds = (rng.standard_normal((20000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((20000, 96)).astype(np.float32))
     qs = (rng.standard_normal((300, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((300, 96)).astype(np.float32))
     index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
-    sp = m.SearchParams(itopk_size=64)
+    sp = m.SearchParams(itopk_size=64, algo="single_cta")
     d32, i32 = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
     index.set_walk_precision(16)
     d16, i16 = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
@@ -159,3 +160,45 @@ def test_fp16_walk_reranks_with_fp32_rows():
     index.set_walk_precision(32)
     d_again, i_again = m.search(sp, index, torch.from_numpy(qs).cuda(), 10)
     assert torch.equal(i_again, i32) and torch.equal(d_again, d32)
+
+
+@pytest.mark.parametrize("nq,itopk,k", [(1, 64, 10), (16, 64, 10), (64, 128, 10), (128, 256, 32), (40, 32, 5)])
+def test_multi_cta_walk_small_batches(nq, itopk, k):
+    """a17: the MULTI_CTA algorithm (search_multi_cta_jit.cuh:56-363) — max(search_width, itopk/32) walkers per query with
+    32-entry lists, parents claimed through a shared traversed table, lists merged + de-duplicated.  Small batches are what
+    the reference selects it for (search_plan.cuh:122-131).  Checked like the reference checks CAGRA (ann_cagra.cuh: recall
+    against exact kNN, min_recall per config): at least the single-CTA walk's recall minus 0.02, unique sorted exact results."""
+    m = _mod()
+    rng = np.random.default_rng(17)
+    A = (rng.standard_normal((8, 64)) / np.sqrt(8)).astype(np.float32)
+    ds = (rng.standard_normal((30000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((30000, 64)).astype(np.float32))
+    qs = (rng.standard_normal((nq, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((nq, 64)).astype(np.float32))
+    index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
+    q = torch.from_numpy(qs).cuda()
+    dm, im = m.search(m.SearchParams(itopk_size=itopk, algo="multi_cta"), index, q, k)
+    ds_, is_ = m.search(m.SearchParams(itopk_size=itopk, algo="single_cta"), index, q, k)
+    da, ia = m.search(m.SearchParams(itopk_size=itopk), index, q, k)       # AUTO: nq < 2 * SMs -> multi-CTA
+    im_n, dm_n = im.cpu().numpy().astype(np.int64), dm.cpu().numpy()
+    assert torch.equal(ia, im) and torch.equal(da, dm)
+    assert all(len(set(r.tolist())) == k for r in im_n) and (im_n >= 0).all() and (im_n < len(ds)).all()
+    np.testing.assert_allclose(dm_n, ((ds[im_n] - qs[:, None, :]) ** 2).sum(-1), rtol=1e-4, atol=1e-6)
+    assert (np.diff(dm_n, axis=1) >= 0).all()
+    gd, gi = oracle.knn(ds, qs, k)
+    r_multi, r_single = oracle.recall(im_n, gi), oracle.recall(is_.cpu().numpy().astype(np.int64), gi)
+    assert r_multi >= max(0.9, r_single - 0.02), (r_multi, r_single)
+
+
+def test_multi_cta_with_bitset_filter():
+    m = _mod()
+    rng = np.random.default_rng(19)
+    A = (rng.standard_normal((8, 64)) / np.sqrt(8)).astype(np.float32)
+    ds = (rng.standard_normal((20000, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((20000, 64)).astype(np.float32))
+    qs = (rng.standard_normal((32, 8)).astype(np.float32) @ A + 0.05 * rng.standard_normal((32, 64)).astype(np.float32))
+    index = m.build(m.IndexParams(graph_degree=32), torch.from_numpy(ds).cuda())
+    keep = rng.random(20000) < 0.5
+    d, i = m.search(m.SearchParams(itopk_size=128, algo="multi_cta"), index, torch.from_numpy(qs).cuda(), 10, filter=_bitset(keep))
+    i = i.cpu().numpy().astype(np.int64)
+    assert keep[i].all(), "a filtered-out node was returned"
+    kept = np.flatnonzero(keep)
+    gd, gi = oracle.knn(ds[kept], qs, 10)
+    assert oracle.recall(i, kept[gi]) >= 0.85
