@@ -403,6 +403,15 @@ cuvsError_t cuvsBruteForceBuild(cuvsResources_t res, DLManagedTensor* dataset_te
       if (index->addr) { delete reinterpret_cast<bf_index*>(index->addr); index->addr = 0; }
       index->addr  = reinterpret_cast<uintptr_t>(bf_build(r, ds, metric, metric_arg));
       index->dtype = ds.dtype;
+    } else if (dl_is_dataset_dtype(ds)) {
+      // float16 / int8 / uint8 (c/src/neighbors/brute_force.cpp:60-110): widened once, the index owns the fp32 copy
+      f32_matrix w;
+      widen_to_f32(r, ds, w);
+      if (index->addr) { delete reinterpret_cast<bf_index*>(index->addr); index->addr = 0; }
+      bf_index* b = bf_build(r, w.t, metric, metric_arg);
+      if (b->data == w.own.data()) b->data_own = std::move(w.own);
+      index->addr  = reinterpret_cast<uintptr_t>(b);
+      index->dtype = ds.dtype;
     } else {
       B2_FAIL("Unsupported dataset DLtensor dtype: %d and bits: %d", ds.dtype.code, ds.dtype.bits);
     }
@@ -429,6 +438,10 @@ cuvsError_t cuvsBruteForceSearch(cuvsResources_t res, cuvsBruteForceIndex_t inde
     B2_EXPECTS(dl_is_c_contiguous(neighbors) && dl_is_c_contiguous(distances), "outputs must be row-major contiguous");
     if (dl_is(queries, kDLFloat, 32)) {
       bf_search(r, *reinterpret_cast<bf_index*>(index->addr), queries, neighbors, distances, prefilter);
+    } else if (dl_is_dataset_dtype(queries) && queries.dtype.bits == index->dtype.bits) {
+      f32_matrix w;
+      widen_to_f32(r, queries, w);
+      bf_search(r, *reinterpret_cast<bf_index*>(index->addr), w.t, neighbors, distances, prefilter);
     } else {
       B2_FAIL("Unsupported queries DLtensor dtype: %d and bits: %d", queries.dtype.code, queries.dtype.bits);
     }

@@ -5,12 +5,60 @@
 // temporary memory comes from the device's stream-ordered pool (cudaMallocAsync) whose release
 // threshold is lifted so that search calls stop hitting the driver after warm-up.
 #include "common.hpp"
+#include "timing.hpp"
+
+#include <cuda_fp16.h>
 
 #include <atomic>
 #include <cstring>
 #include <string>
 
 namespace b200 {
+
+template <typename T>
+__global__ void widen_kernel(const T* __restrict__ in, int64_t n, float* __restrict__ out)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+
+void widen_to_f32(resources* res, const DLTensor& src, f32_matrix& out)
+{
+  B2_EXPECTS(src.ndim == 2 && dl_is_c_contiguous(src), "matrix must be a row-major 2-D tensor");
+  B2_EXPECTS(dl_is_dataset_dtype(src), "Unsupported DLtensor dtype: %d and bits: %d", src.dtype.code, src.dtype.bits);
+  out.t        = src;
+  out.shape[0] = src.shape[0];
+  out.shape[1] = src.shape[1];
+  out.t.shape  = out.shape;
+  out.t.strides = nullptr;
+  if (dl_is(src, kDLFloat, 32)) return;
+  const int64_t count = src.shape[0] * src.shape[1];
+  const size_t esize  = src.dtype.bits / 8;
+  out.own.alloc(static_cast<size_t>(std::max<int64_t>(count, 1)));
+  out.widened = true;
+  auto s      = res->stream;
+  const void* in = dl_ptr<char>(src);
+  dbuf<uint8_t> stage;
+  const bool dev = dl_is_device(src) && src.device.device_type != kDLCUDAHost;
+  if (!dev && count) {
+    stage.alloc(static_cast<size_t>(count) * esize, s);
+    B2_CUDA(cudaMemcpyAsync(stage.data(), in, static_cast<size_t>(count) * esize, cudaMemcpyHostToDevice, s));
+    in = stage.data();
+  }
+  if (count) {
+    const unsigned grid = static_cast<unsigned>((count + 255) / 256);
+    count_launch();
+    if (dl_is(src, kDLFloat, 16)) widen_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(in), count, out.own.data());
+    else if (dl_is(src, kDLInt, 8)) widen_kernel<int8_t><<<grid, 256, 0, s>>>(static_cast<const int8_t*>(in), count, out.own.data());
+    else widen_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(in), count, out.own.data());
+    B2_CUDA(cudaGetLastError());
+  }
+  out.t.data        = out.own.data();
+  out.t.byte_offset = 0;
+  out.t.dtype       = DLDataType{kDLFloat, 32, 1};
+  out.t.device      = DLDevice{kDLCUDA, res->device};
+}
+
 
 static thread_local std::string g_last_error;
 static std::atomic<int> g_log_level{CUVS_LOG_LEVEL_INFO};

@@ -906,15 +906,22 @@ static cagra_index& cagra_of(cuvsCagraIndex_t index)
   return *reinterpret_cast<cagra_index*>(index->addr);
 }
 
-static void set_dataset(resources* r, cagra_index& idx, const DLTensor& ds)
+static void set_dataset(resources* r, cagra_index& idx, const DLTensor& ds_in)
 {
-  B2_EXPECTS(dl_is(ds, kDLFloat, 32), "cagra: only float32 datasets are supported by this build");
+  // float16 / int8 / uint8 datasets (c/src/neighbors/cagra.cpp:245-264) are widened to fp32 rows the index owns
+  B2_EXPECTS(dl_is_dataset_dtype(ds_in), "Unsupported dataset DLtensor dtype: %d and bits: %d", ds_in.dtype.code, ds_in.dtype.bits);
+  f32_matrix w;
+  widen_to_f32(r, ds_in, w);
+  const DLTensor& ds = w.t;
   B2_EXPECTS(ds.ndim == 2 && dl_is_c_contiguous(ds), "dataset must be a row-major 2-D tensor");
   idx.n   = ds.shape[0];
   idx.dim = static_cast<int>(ds.shape[1]);
   idx.ld  = (idx.dim + 3) & ~3;  // rows padded to 16 bytes (cagra.hpp:610)
   const bool dev = dl_is_device(ds) && ds.device.device_type != kDLCUDAHost;
-  if (dev && idx.ld == idx.dim && (reinterpret_cast<uintptr_t>(dl_ptr<float>(ds)) & 15) == 0) {
+  if (w.widened && idx.ld == idx.dim) {
+    idx.data_own = std::move(w.own);
+    idx.data     = idx.data_own.data();
+  } else if (dev && idx.ld == idx.dim && (reinterpret_cast<uintptr_t>(dl_ptr<float>(ds)) & 15) == 0) {
     idx.data = dl_ptr<float>(ds);  // non-owning view, like the reference's strided_dataset view
   } else {
     idx.data_own.alloc(static_cast<size_t>(idx.n) * idx.ld);
@@ -1055,7 +1062,7 @@ cuvsError_t cuvsCagraIndexFromArgs(cuvsResources_t res, cuvsDistanceType metric,
     B2_CUDA(cudaStreamSynchronize(r->stream));
     if (index->addr) delete reinterpret_cast<cagra_index*>(index->addr);
     index->addr  = reinterpret_cast<uintptr_t>(idx.release());
-    index->dtype = DLDataType{kDLFloat, 32, 1};
+    index->dtype = dataset_t->dl_tensor.dtype;
   });
 }
 
@@ -1110,7 +1117,7 @@ cuvsError_t cuvsCagraBuild(cuvsResources_t res, cuvsCagraIndexParams_t params, D
     idx->degree = degree;
     if (index->addr) delete reinterpret_cast<cagra_index*>(index->addr);
     index->addr  = reinterpret_cast<uintptr_t>(idx.release());
-    index->dtype = DLDataType{kDLFloat, 32, 1};
+    index->dtype = dataset_t->dl_tensor.dtype;
   });
 }
 
@@ -1145,7 +1152,9 @@ cuvsError_t cuvsCagraSearch(cuvsResources_t res, cuvsCagraSearchParams_t params,
       n_bits = ft->dl_tensor.shape[0] * 32;
     }
     const bool u32 = dl_is(neighbors, kDLUInt, 32);
-    cagra_search(r, idx, *params, dl_ptr<float>(queries), queries.shape[0], static_cast<int>(neighbors.shape[1]),
+    f32_matrix wq;
+    widen_to_f32(r, queries, wq);
+    cagra_search(r, idx, *params, dl_ptr<float>(wq.t), queries.shape[0], static_cast<int>(neighbors.shape[1]),
                  u32 ? dl_ptr<uint32_t>(neighbors) : nullptr, u32 ? nullptr : dl_ptr<int64_t>(neighbors), dl_ptr<float>(distances),
                  keep, n_bits);
   });

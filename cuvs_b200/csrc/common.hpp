@@ -214,6 +214,27 @@ struct dl_row_slice {
   dl_row_slice(const dl_row_slice&) = delete;
 };
 
+/**
+ * fp32 view of a dataset / query matrix given as float32, float16, int8 or uint8 — the element types the reference's C ABI
+ * dispatches on (c/src/neighbors/ivf_pq.cpp:80-103, ivf_flat.cpp, brute_force.cpp:60-110, cagra.cpp:245-264).  float32
+ * passes through untouched; the narrower types are widened into an owned device buffer (host sources are staged), values
+ * unchanged — the reference maps int8 / uint8 through utils::mapping<float> and scales the distances back
+ * (ivf_pq_search.cuh:1043), which is the same arithmetic in different units.  All kernels of this library then run on fp32.
+ */
+struct f32_matrix {
+  DLTensor t{};
+  int64_t shape[2] = {0, 0};
+  owned<float> own;      // non-empty when the source was widened
+  bool widened = false;
+  f32_matrix() = default;
+  f32_matrix(const f32_matrix&) = delete;
+};
+inline bool dl_is_dataset_dtype(const DLTensor& t)
+{
+  return dl_is(t, kDLFloat, 32) || dl_is(t, kDLFloat, 16) || dl_is(t, kDLInt, 8) || dl_is(t, kDLUInt, 8);
+}
+void widen_to_f32(struct resources* res, const DLTensor& src, f32_matrix& out);
+
 /** Fill a caller-provided DLManagedTensor as a non-owning row-major view (used by index getters). */
 void dl_fill_view(DLManagedTensor* out, void* data, int device, DLDataType dt, int ndim, const int64_t* shape);
 

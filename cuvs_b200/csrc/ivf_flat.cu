@@ -493,9 +493,11 @@ cuvsError_t cuvsIvfFlatBuild(cuvsResources_t res, cuvsIvfFlatIndexParams_t param
     auto r = as_res(res);
     B2_EXPECTS(params && dataset && index, "null argument");
     const DLTensor& ds = dataset->dl_tensor;
-    B2_EXPECTS(dl_is(ds, kDLFloat, 32), "Unsupported dataset DLtensor dtype: %d and bits: %d", ds.dtype.code, ds.dtype.bits);
+    B2_EXPECTS(dl_is_dataset_dtype(ds), "Unsupported dataset DLtensor dtype: %d and bits: %d", ds.dtype.code, ds.dtype.bits);
     if (index->addr) { delete reinterpret_cast<ivf_flat_index*>(index->addr); index->addr = 0; }
-    index->addr  = reinterpret_cast<uintptr_t>(ivf_flat_build(r, *params, ds));
+    f32_matrix w;  // float16 / int8 / uint8 datasets (c/src/neighbors/ivf_flat.cpp dtype switch) are widened to fp32 rows
+    widen_to_f32(r, ds, w);
+    index->addr  = reinterpret_cast<uintptr_t>(ivf_flat_build(r, *params, w.t));
     index->dtype = ds.dtype;
   });
 }
@@ -527,7 +529,9 @@ cuvsError_t cuvsIvfFlatSearch(cuvsResources_t res, cuvsIvfFlatSearchParams_t par
       keep   = dl_ptr<uint32_t>(ft->dl_tensor);
       n_bits = ft->dl_tensor.shape[0] * 32;
     }
-    ivf_flat_search(r, idx, params->n_probes, queries, neighbors, distances, keep, n_bits);
+    f32_matrix w;
+    widen_to_f32(r, queries, w);
+    ivf_flat_search(r, idx, params->n_probes, w.t, neighbors, distances, keep, n_bits);
   });
 }
 
@@ -537,8 +541,12 @@ cuvsError_t cuvsIvfFlatExtend(cuvsResources_t res, DLManagedTensor* new_vectors,
     auto r    = as_res(res);
     auto& idx = flat_of(index);
     B2_EXPECTS(new_vectors != nullptr, "new_vectors is null");
-    const DLTensor& v = new_vectors->dl_tensor;
-    B2_EXPECTS(dl_is(v, kDLFloat, 32) && v.ndim == 2 && v.shape[1] == idx.dim && dl_is_c_contiguous(v), "new_vectors must be [n, dim] float32 row-major");
+    B2_EXPECTS(dl_is_dataset_dtype(new_vectors->dl_tensor), "Unsupported new_vectors DLtensor dtype: %d and bits: %d",
+               new_vectors->dl_tensor.dtype.code, new_vectors->dl_tensor.dtype.bits);
+    f32_matrix wv;
+    widen_to_f32(r, new_vectors->dl_tensor, wv);
+    const DLTensor& v = wv.t;
+    B2_EXPECTS(dl_is(v, kDLFloat, 32) && v.ndim == 2 && v.shape[1] == idx.dim && dl_is_c_contiguous(v), "new_vectors must be [n, dim] row-major");
     const int64_t n = v.shape[0];
     dbuf<int64_t> ids_dev;
     const int64_t* ids = nullptr;

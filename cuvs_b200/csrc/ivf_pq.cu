@@ -65,7 +65,10 @@ struct ivf_pq_index {
   owned<float> pq_centers;   // PER_SUBSPACE [pq_dim, pq_len, book] | PER_CLUSTER [n_lists, pq_len, book]
   tc_rows centers_tc;
   list_layout lists;
-  owned<uint8_t> codes;  // [rows_total, pq_dim], one code per byte
+  // [rows_total, pq_dim], one code per byte.  When the index is served by the code-streaming scan the stream below IS the
+  // index and this flat copy is dropped after (re)building it; ensure_flat_codes() re-materialises it for the paths that
+  // want rows (getters, extend, serialize, the LUT kernel).
+  mutable owned<uint8_t> codes;
   owned<int64_t> ids;    // [rows_total], kPadId on padding rows
   // decoded side (path B)
   int Kp = 0;
@@ -82,6 +85,15 @@ struct ivf_pq_index {
 namespace {
 
 inline unsigned blocks_for(int64_t n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+void ensure_flat_codes(resources* res, const ivf_pq_index& idx)
+{
+  const size_t need = static_cast<size_t>(std::max<int64_t>(idx.lists.rows_total, 1)) * idx.pq_dim;
+  if (idx.codes.data() != nullptr && idx.codes.size() >= need) return;
+  B2_EXPECTS(idx.cstream.data() != nullptr, "ivf_pq: the index holds neither flat codes nor a code stream");
+  idx.codes.alloc(need);
+  pq_stream_to_flat(res->stream, idx.cstream.data(), idx.lists.rows_total, idx.pq_dim, idx.codes.data());
+}
 bool is_l2(cuvsDistanceType m) { return m == L2Expanded || m == L2SqrtExpanded || m == L2Unexpanded || m == L2SqrtUnexpanded; }
 bool is_ip(cuvsDistanceType m) { return m == InnerProduct || m == CosineExpanded; }
 
@@ -570,6 +582,11 @@ void refresh_decoded(resources* res, ivf_pq_index& idx)
     idx.cb_words.alloc(static_cast<size_t>(idx.pq_dim / 32) * 256 * 32);
     pq_stream_build(s, idx.codes.data(), idx.ids.data(), kPadId, R, idx.pq_dim, idx.pq_centers.data(), is_ip(idx.metric),
                     idx.cstream.data(), idx.cb_words.data());
+    static const bool keep_flat = getenv("CUVS_B200_PQ_KEEP_FLAT") != nullptr;
+    if (!keep_flat && R > 0) {  // the stream is the index: pq_dim + 4 bytes per vector (+ 8 for the id)
+      B2_CUDA(cudaStreamSynchronize(s));
+      idx.codes.release();
+    }
     return;
   }
   idx.yhat.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * idx.Kp);
@@ -662,6 +679,7 @@ void ivf_pq_extend(resources* res, ivf_pq_index& idx, const DLTensor& t, const i
   count_launch();
   fill_i64_kernel<<<blocks_for(nl.rows_total, 256), 256, 0, s>>>(nids.data(), nl.rows_total, kPadId);
   if (idx.lists.rows_total > 0) {
+    ensure_flat_codes(res, idx);
     dbuf<int64_t> dst_old(static_cast<size_t>(idx.lists.rows_total), s);
     count_launch(2);
     remap_rows_kernel<<<idx.n_lists, 128, 0, s>>>(idx.lists.d_offsets.data(), nl.d_offsets.data(), idx.lists.d_sizes.data(), idx.n_lists,
@@ -891,6 +909,7 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
                      idx.Kp, idx.hx.data(), pb.items.data(), pb.max_items, pb.n_items.data(), KC, passes, cs.data(), cp.data(), KCW, bkeys.data() ? &bnd : nullptr);
     }
   } else {
+    ensure_flat_codes(res, idx);
     const int book      = idx.book();
     const size_t lut_b  = sp.lut_dtype == CUDA_R_32F ? 4 : (sp.lut_dtype == CUDA_R_16F ? 2 : 1);
     const size_t smem   = ((static_cast<size_t>(idx.pq_dim) * book * lut_b + 15) & ~size_t(15)) + 2 * idx.rot_dim * sizeof(float) +
@@ -1087,6 +1106,7 @@ cuvsError_t cuvsIvfPqIndexUnpackContiguousListData(cuvsResources_t res, cuvsIvfP
     const int64_t n_take = oc.shape[0];
     B2_EXPECTS(static_cast<int64_t>(offset) + n_take <= idx.lists.h_sizes[label], "offset + n_rows exceeds the list size");
     if (n_take == 0) return;
+    ensure_flat_codes(r, idx);
     pack_codes_kernel<<<blocks_for(n_take, 128), 128, 0, r->stream>>>(idx.codes.data() + (idx.lists.h_offsets[label] + offset) * idx.pq_dim,
                                                                       n_take, idx.pq_dim, idx.pq_bits, out_ld, dl_ptr<uint8_t>(oc));
     B2_CUDA(cudaGetLastError());
@@ -1109,9 +1129,11 @@ cuvsError_t cuvsIvfPqBuild(cuvsResources_t res, cuvsIvfPqIndexParams_t params, D
     auto r = as_res(res);
     B2_EXPECTS(params && dataset && index, "null argument");
     const DLTensor& ds = dataset->dl_tensor;
-    B2_EXPECTS(dl_is(ds, kDLFloat, 32), "Unsupported dataset DLtensor dtype: %d and bits: %d", ds.dtype.code, ds.dtype.bits);
+    B2_EXPECTS(dl_is_dataset_dtype(ds), "Unsupported dataset DLtensor dtype: %d and bits: %d", ds.dtype.code, ds.dtype.bits);
     if (index->addr) { delete reinterpret_cast<ivf_pq_index*>(index->addr); index->addr = 0; }
-    index->addr  = reinterpret_cast<uintptr_t>(ivf_pq_build(r, *params, ds));
+    f32_matrix w;  // float16 / int8 / uint8 datasets (c/src/neighbors/ivf_pq.cpp:80-103) are widened to fp32 rows
+    widen_to_f32(r, ds, w);
+    index->addr  = reinterpret_cast<uintptr_t>(ivf_pq_build(r, *params, w.t));
     index->dtype = ds.dtype;
   });
 }
@@ -1192,10 +1214,12 @@ cuvsError_t cuvsIvfPqSearch(cuvsResources_t res, cuvsIvfPqSearchParams_t params,
     B2_EXPECTS(dl_is_device(distances), "distances should have device compatible memory");
     B2_EXPECTS(dl_is(neighbors, kDLInt, 64), "neighbors should be of type int64_t");
     B2_EXPECTS(dl_is(distances, kDLFloat, 32), "distances should be of type float32");
-    B2_EXPECTS(dl_is(queries, kDLFloat, 32), "Unsupported queries DLtensor dtype: %d and bits: %d", queries.dtype.code, queries.dtype.bits);
+    B2_EXPECTS(dl_is_dataset_dtype(queries), "Unsupported queries DLtensor dtype: %d and bits: %d", queries.dtype.code, queries.dtype.bits);
     B2_EXPECTS(queries.ndim == 2 && neighbors.ndim == 2 && distances.ndim == 2, "queries/neighbors/distances must be 2-D");
     B2_EXPECTS(dl_is_c_contiguous(queries) && dl_is_c_contiguous(neighbors) && dl_is_c_contiguous(distances), "tensors must be row-major contiguous");
-    ivf_pq_search(r, idx, *params, queries, neighbors, distances);
+    f32_matrix w;
+    widen_to_f32(r, queries, w);
+    ivf_pq_search(r, idx, *params, w.t, neighbors, distances);
   });
 }
 
@@ -1205,8 +1229,12 @@ cuvsError_t cuvsIvfPqExtend(cuvsResources_t res, DLManagedTensor* new_vectors, D
     auto r    = as_res(res);
     auto& idx = pq_of(index);
     B2_EXPECTS(new_vectors != nullptr, "new_vectors is null");
-    const DLTensor& v = new_vectors->dl_tensor;
-    B2_EXPECTS(dl_is(v, kDLFloat, 32) && v.ndim == 2 && v.shape[1] == idx.dim && dl_is_c_contiguous(v), "new_vectors must be [n, dim] float32 row-major");
+    B2_EXPECTS(dl_is_dataset_dtype(new_vectors->dl_tensor), "Unsupported new_vectors DLtensor dtype: %d and bits: %d",
+               new_vectors->dl_tensor.dtype.code, new_vectors->dl_tensor.dtype.bits);
+    f32_matrix wv;
+    widen_to_f32(r, new_vectors->dl_tensor, wv);
+    const DLTensor& v = wv.t;
+    B2_EXPECTS(dl_is(v, kDLFloat, 32) && v.ndim == 2 && v.shape[1] == idx.dim && dl_is_c_contiguous(v), "new_vectors must be [n, dim] row-major");
     const int64_t n = v.shape[0];
     dbuf<int64_t> ids_dev;
     const int64_t* ids = nullptr;
@@ -1320,6 +1348,7 @@ cuvsError_t cuvsIvfPqSerialize(cuvsResources_t res, const char* filename, cuvsIv
     std::vector<uint8_t> codes;
     std::vector<int64_t> ids;
     const int C = 128 / idx.pq_bits;
+    ensure_flat_codes(r, idx);
     for (uint32_t l = 0; l < idx.n_lists; ++l) {
       const int64_t sz = idx.lists.h_sizes[l];
       npy::write_scalar<uint32_t>(os, static_cast<uint32_t>(sz));

@@ -16,10 +16,10 @@
 //                          swizzled K-major operand tile (bf16 row = 256 B).  4.5 shared-memory wavefronts per row.
 //   warp 1      MMA        D[128 rows x NQ queries] (+)= Y_tile . R^T : tcgen05.mma kind::f16, M = 128 (rows), N = NQ, 8 K-steps
 //                          + 1 step that adds -|y|^2/2 (three bf16 pieces x ones); accumulators in a 4-deep TMEM ring
-//   warps 10-13 epilogue   thread = row, columns = queries: tcgen05.ld 32 columns, compare against the queries' running
+//   warps 10-17 epilogue   thread = row, columns = queries: tcgen05.ld 32 columns, compare against the queries' running
 //                          thresholds (shared memory), push the rare hits into per-query candidate buffers; a buffer that
-//                          overflows is compacted to its KC best by one warp (redux-based selection) and the threshold
-//                          tightened; one named barrier per tile.
+//                          overflows is compacted to its KC best by one warp (rank by counting) and the threshold
+//                          tightened; one named barrier per round of acc/2 tiles.
 //
 // With few probing queries per list (100M rows / 16k lists / 10k-query batches: ~30) the accumulator is 128 x 32..64
 // instead of the 128 x 128 of the query-major kernel (scan_tc.cu), the rows fill the MMA's M side completely, and HBM
@@ -30,21 +30,24 @@
 #include "timing.hpp"
 
 #include <cuda.h>
+#include <unistd.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace b200 {
 namespace {
 
 constexpr int kDecWarps   = 8;
-constexpr int kEpiWarps   = 4;
+constexpr int kEpiWarps   = 8;   // two per TMEM lane quarter: each owns every other 32-column chunk of the accumulator
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreads    = 64 + 32 * kDecWarps + kEpiThreads;  // 448
+constexpr int kThreads    = 64 + 32 * kDecWarps + kEpiThreads;  // 576
 constexpr int kEpiWarp0   = 2 + kDecWarps;                      // first epilogue warp (10: warp & 3 covers all TMEM quarters)
 constexpr int kDecStages  = 2;
-constexpr int kAcc        = 4;   // TMEM accumulator ring
+constexpr int kMaxAcc     = 8;   // TMEM accumulator ring: min(8, 512 / NQ) buffers of NQ columns
 constexpr int kSched      = 4;   // work-item ring
 constexpr int kMaxCStages = 8;
 constexpr int kDecTile    = 128 * 128;  // one k-block of the decoded tile: 128 rows x 64 bf16, SWIZZLE_128B
@@ -70,7 +73,37 @@ struct pq_args {
   int cap;      // candidate buffer entries per query (KC < cap <= 64)
   int cstages;  // code ring depth
   int blk;      // bytes of one tile block of the stream
+  int dbg_mode;   // CUVS_B200_PQ_DEBUG value: 2 = the epilogue only drains TMEM (no filtering): pipeline-only bisection
+  uint32_t* dbg;  // CUVS_B200_PQ_DEBUG=1: mapped host memory, [grid][8] = {code of the wait that timed out, parity, item, tile, ...}
 };
+
+// Debug wait: identical to ptx::mbar_wait unless P.dbg is set; then a wait that does not complete within ~2 s records where
+// it is stuck (role/barrier code, parity, progress counters) in mapped host memory and traps, so a deadlock becomes a report.
+__device__ __forceinline__ void wait_dbg(uint32_t* dbg, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t a, uint32_t b)
+{
+  if (dbg == nullptr) { ptx::mbar_wait(bar, parity); return; }
+  for (uint32_t spin = 0; spin < 4000000u; ++spin) {
+    uint32_t ok;
+    asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(ptx::smem_u32(bar)), "r"(parity)
+      : "memory");
+    if (ok) return;
+    __nanosleep(500);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t* d = dbg + blockIdx.x * 16;
+    if (atomicCAS(d, 0u, code) == 0u) { d[1] = parity; d[2] = a; d[3] = b; d[4] = threadIdx.x >> 5; }
+    __threadfence_system();
+  }
+  __nanosleep(100000000);
+  __trap();
+}
 
 __device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred)
 {
@@ -106,11 +139,13 @@ struct layout {
   static constexpr int off_thr    = off_cb + cb_bytes;
   static constexpr int off_cnt    = off_thr + NQ * 4;
   static constexpr int off_bars   = off_cnt + NQ * 4;
-  static constexpr int n_bars     = 2 * kMaxCStages + 2 * kDecStages + 2 + 2 * kAcc + 2 * kSched;
+  static constexpr int acc        = 512 / NQ < kMaxAcc ? 512 / NQ : kMaxAcc;  // accumulator buffers
+  static constexpr int tb         = acc / 2;                                   // tiles per epilogue round (one barrier per round)
+  static constexpr int n_bars     = 2 * kMaxCStages + 2 * kDecStages + 2 + 2 * kMaxAcc + 2 * kSched;
   static constexpr int off_item   = off_bars + n_bars * 8;
   static constexpr int off_tmem   = off_item + kSched * 4;
   static constexpr int off_cand   = (off_tmem + 4 + 15) / 16 * 16;   // [NQ][cap] uint2, then the code ring
-  static constexpr int tmem_cols  = kAcc * NQ;
+  static constexpr int tmem_cols  = acc * NQ;
   static_assert(q_tile % 1024 == 0 && dec_stage % 1024 == 0, "operand tiles need 1024-byte alignment");
 };
 
@@ -135,12 +170,12 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
   uint64_t* q_full  = d_empty + kDecStages;
   uint64_t* q_empty = q_full + 1;
   uint64_t* t_full  = q_empty + 1;
-  uint64_t* t_empty = t_full + kAcc;
-  uint64_t* s_full  = t_empty + kAcc;
+  uint64_t* t_empty = t_full + kMaxAcc;
+  uint64_t* s_full  = t_empty + kMaxAcc;
   uint64_t* s_empty = s_full + kSched;
   int* s_item       = reinterpret_cast<int*>(smem_raw + L::off_item);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L::off_tmem);
-  uint2* sCand    = reinterpret_cast<uint2*>(smem_raw + L::off_cand);
+  unsigned long long* sCand = reinterpret_cast<unsigned long long*>(smem_raw + L::off_cand);  // okey(t) << 32 | ~pos
   uint8_t* sCode  = smem_raw + L::off_cand + NQ * P.cap * 8;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -162,7 +197,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     }
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(q_empty, 1);
-    for (int s = 0; s < kAcc; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       ptx::mbar_init(&t_full[s], 1);
       ptx::mbar_init(&t_empty[s], kEpiWarps);
     }
@@ -189,7 +224,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     // ------------------------------------------------------------------ producer (whole warp loops, one elected lane issues)
     uint32_t cs = 0, cph = 0, qph = 0, ss = 0, sp = 0;
     for (;;) {
-      ptx::mbar_wait(&s_empty[ss], sp ^ 1);
+      wait_dbg(P.dbg, &s_empty[ss], sp ^ 1, 0x101, ss, 0);
       int it = 0;
       if (lane == 0) {
         it = atomicAdd(P.sched, 1);
@@ -204,7 +239,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       item.a_row0  = __shfl_sync(0xffffffffu, item.a_row0, 0);
       item.b_row0  = __shfl_sync(0xffffffffu, item.b_row0, 0);
       item.n_tiles = __shfl_sync(0xffffffffu, item.n_tiles, 0);
-      ptx::mbar_wait(q_empty, qph ^ 1);
+      wait_dbg(P.dbg, q_empty, qph ^ 1, 0x102, static_cast<uint32_t>(it), 0);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(q_full, L::q_bytes);
 #pragma unroll
@@ -216,7 +251,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       qph ^= 1;
       const uint8_t* src = P.stream + static_cast<int64_t>(item.b_row0 >> 7) * P.blk;
       for (uint32_t t = 0; t < item.n_tiles; ++t) {
-        ptx::mbar_wait(&c_empty[cs], cph ^ 1);
+        wait_dbg(P.dbg, &c_empty[cs], cph ^ 1, 0x103, static_cast<uint32_t>(it), t);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&c_full[cs], static_cast<uint32_t>(P.blk));
           ptx::bulk_load_1d(sCode + cs * P.blk, src + static_cast<int64_t>(t) * P.blk, static_cast<uint32_t>(P.blk), &c_full[cs]);
@@ -232,17 +267,17 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_u32(sOnes));
     uint32_t ds = 0, dph = 0, acc = 0, aph = 0, qph = 0, ss = 0, sp = 0;
     for (;;) {
-      ptx::mbar_wait(&s_full[ss], sp);
+      wait_dbg(P.dbg, &s_full[ss], sp, 0x201, ss, 0);
       const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
       const uint32_t n_tiles = __shfl_sync(0xffffffffu, P.items[it].n_tiles, 0);
-      ptx::mbar_wait(q_full, qph);
+      wait_dbg(P.dbg, q_full, qph, 0x202, static_cast<uint32_t>(it), 0);
       ptx::tc_fence_after_sync();
       for (uint32_t t = 0; t < n_tiles; ++t) {
-        ptx::mbar_wait(&t_empty[acc], aph ^ 1);
-        ptx::mbar_wait(&d_full[ds], dph);
+        wait_dbg(P.dbg, &t_empty[acc], aph ^ 1, 0x203, static_cast<uint32_t>(it), t);
+        wait_dbg(P.dbg, &d_full[ds], dph, 0x204, static_cast<uint32_t>(it), t);
         ptx::tc_fence_after_sync();
         if (ptx::elect_one()) {
           const uint32_t d_tmem = tmem_base + acc * NQ;
@@ -264,7 +299,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           ptx::mma_commit(&t_full[acc]);
         }
         if (++ds == kDecStages) { ds = 0; dph ^= 1; }
-        if (++acc == kAcc) { acc = 0; aph ^= 1; }
+        if (++acc == L::acc) { acc = 0; aph ^= 1; }
       }
       if (ptx::elect_one()) ptx::mma_commit(q_empty);
       qph ^= 1;
@@ -278,7 +313,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     const uint8_t* cb_lane = reinterpret_cast<const uint8_t*>(sCb) + lane * 4;
     uint32_t cs = 0, cph = 0, ds = 0, dph = 0, ss = 0, sp = 0;
     for (;;) {
-      ptx::mbar_wait(&s_full[ss], sp);
+      wait_dbg(P.dbg, &s_full[ss], sp, 0x301, ss, 0);
       const int it = s_item[ss];
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
@@ -286,7 +321,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       if (it < 0) break;
       const uint32_t n_tiles = P.items[it].n_tiles;
       for (uint32_t t = 0; t < n_tiles; ++t) {
-        ptx::mbar_wait(&c_full[cs], cph);
+        wait_dbg(P.dbg, &c_full[cs], cph, 0x302, static_cast<uint32_t>(it), t);
         const uint8_t* cst = sCode + cs * P.blk;
         uint4 cw[NKB];
 #pragma unroll
@@ -296,7 +331,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
         if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);  // the codes are in registers: hand the ring slot back
         if (++cs == ncs) { cs = 0; cph ^= 1; }
 
-        ptx::mbar_wait(&d_empty[ds], dph ^ 1);
+        wait_dbg(P.dbg, &d_empty[ds], dph ^ 1, 0x303, static_cast<uint32_t>(it), t);
         uint8_t* dst = sDec + ds * L::dec_stage + (2 * dw) * 1024;
 #pragma unroll
         for (int h = 0; h < NKB; ++h) {
@@ -336,53 +371,57 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     // ------------------------------------------------------------------ epilogue: thread = list row, columns = queries
     const int ew      = warp - kEpiWarp0;
     const int quarter = warp & 3;
+    const int half    = ew >> 2;  // this warp takes the chunks c with c % 2 == half (NQ = 32: the second half only joins the barriers)
     const int row     = quarter * 32 + lane;
     const int te      = static_cast<int>(threadIdx.x) - 32 * kEpiWarp0;  // 0..127
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int cap = P.cap, KC = P.KC;
     const int kth = (P.kth > 0 && P.kth < KC) ? P.kth : KC;
     constexpr int NCH = NQ / 32;
+    constexpr int MYCH = NCH >= 2 ? NCH / 2 : 1;  // chunks per epilogue warp
     uint32_t acc = 0, aph = 0, ss = 0, sp = 0;
 
-    // compaction of column `col` by one warp: the KC best of its buffer, lane j ends up with the j-th best
-    // (key = order(t) << 32 | ~pos, 0 = none); returns the number kept
-    auto select_best = [&](int col, unsigned long long& mine) -> int {
+    // Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l and l + 32 (as 64-bit keys:
+    // order(t) << 32 | ~pos, unique, 0 = none); every entry is broadcast from shared memory and each lane counts how many beat
+    // its own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + two compare-adds.
+    auto rank_select = [&](int col, unsigned long long& k0, unsigned long long& k1, int& r0, int& r1) -> int {
       const int n = min(sCnt[col], cap);
-      unsigned long long k0 = 0, k1 = 0;
-      if (lane < n) { const uint2 e = sCand[col * cap + lane]; k0 = (static_cast<unsigned long long>(okey(e.x)) << 32) | (~e.y); }
-      if (lane + 32 < n) { const uint2 e = sCand[col * cap + lane + 32]; k1 = (static_cast<unsigned long long>(okey(e.x)) << 32) | (~e.y); }
-      mine   = 0;
-      int nk = 0;
-      for (int j = 0; j < KC; ++j) {
-        const unsigned long long m = k0 > k1 ? k0 : k1;
-        const uint32_t mh = static_cast<uint32_t>(m >> 32);
-        const uint32_t hi = __reduce_max_sync(0xffffffffu, mh);
-        if (hi == 0) break;
-        const uint32_t lo = __reduce_max_sync(0xffffffffu, mh == hi ? static_cast<uint32_t>(m) : 0u);
-        const unsigned long long best = (static_cast<unsigned long long>(hi) << 32) | lo;
-        if (k0 == best) k0 = 0;
-        else if (k1 == best) k1 = 0;
-        if (lane == j) mine = best;
-        nk = j + 1;
+      const unsigned long long* buf = sCand + col * cap;
+      k0 = lane < n ? buf[lane] : 0ull;
+      k1 = lane + 32 < n ? buf[lane + 32] : 0ull;
+      r0 = r1 = 0;
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const unsigned long long ki = buf[i];
+        r0 += ki > k0 ? 1 : 0;
+        r1 += ki > k1 ? 1 : 0;
       }
-      return nk;
+      return n;
     };
+    // compaction: keep the KC best at the front, tighten the column's threshold to its kth best
     auto compact = [&](int col) {
-      unsigned long long mine;
-      const int nk = select_best(col, mine);
+      unsigned long long k0, k1;
+      int r0, r1;
+      const int n = rank_select(col, k0, k1, r0, r1);
       __syncwarp();
-      if (lane < nk) sCand[col * cap + lane] = make_uint2(okey_inv(static_cast<uint32_t>(mine >> 32)), ~static_cast<uint32_t>(mine));
-      const uint32_t kbits = __shfl_sync(0xffffffffu, okey_inv(static_cast<uint32_t>(mine >> 32)), kth - 1);
-      if (lane == 0) {
-        sCnt[col] = nk;
-        if (nk >= kth) sThr[col] = fmaxf(sThr[col], __uint_as_float(kbits));
+      unsigned long long* buf = sCand + col * cap;
+      if (k0 != 0ull && r0 < KC) buf[r0] = k0;
+      if (k1 != 0ull && r1 < KC) buf[r1] = k1;
+      if (n >= kth) {
+        if (k0 != 0ull && r0 == kth - 1) sThr[col] = fmaxf(sThr[col], __uint_as_float(okey_inv(static_cast<uint32_t>(k0 >> 32))));
+        if (k1 != 0ull && r1 == kth - 1) sThr[col] = fmaxf(sThr[col], __uint_as_float(okey_inv(static_cast<uint32_t>(k1 >> 32))));
       }
+      if (lane == 0) sCnt[col] = min(n, KC);
       __syncwarp();
     };
 
+    auto mark = [&](uint32_t stage) {
+      if (P.dbg != nullptr && lane == 0) { reinterpret_cast<volatile uint32_t*>(P.dbg)[blockIdx.x * 16 + 8 + ew] = stage; __threadfence_system(); }
+    };
     for (;;) {
-      ptx::mbar_wait(&s_full[ss], sp);
+      wait_dbg(P.dbg, &s_full[ss], sp, 0x401, ss, 0);
       const int it = s_item[ss];
+      mark(1);
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
@@ -403,89 +442,135 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
         sThr[col] = thr;
         sCnt[col] = 0;
       }
+      mark(2);
       ptx::named_bar_sync(1, kEpiThreads);
+      mark(3);
 
-      for (uint32_t t = 0; t < item.n_tiles; ++t) {
-        ptx::mbar_wait(&t_full[acc], aph);
-        ptx::tc_fence_after_sync();
-        const uint32_t pos   = item.b_row0 + t * 128 + row;
-        const uint32_t taddr = t_lane + acc * NQ;
-        uint32_t pend[NCH];
-        // one chunk of 32 query columns: returns the columns whose candidate could not be stored (buffer full)
-        auto do_chunk = [&](int c, uint32_t only) -> uint32_t {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
-          ptx::tmem_ld_wait();
-          const float4* th4 = reinterpret_cast<const float4*>(sThr + c * 32);
-          float th[32];
+      // one chunk of 32 query columns of one tile: returns the columns whose candidate could not be stored (buffer full)
+      auto do_chunk = [&](uint32_t taddr, uint32_t pos, int c, uint32_t only) -> uint32_t {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        const float4* th4 = reinterpret_cast<const float4*>(sThr + c * 32);
+        float d[32];  // margin over the column's threshold: a candidate iff d > 0 (exact: the difference of two floats keeps its sign)
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x = th4[j4];
-            th[4 * j4] = x.x; th[4 * j4 + 1] = x.y; th[4 * j4 + 2] = x.z; th[4 * j4 + 3] = x.w;
-          }
-          float m = -INFINITY;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 x = th4[j4];
+          d[4 * j4]     = __uint_as_float(v[4 * j4]) - x.x;
+          d[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) - x.y;
+          d[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) - x.z;
+          d[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) - x.w;
+        }
+        float q[4];  // per group of 8 columns
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]) - th[j]);
-          uint32_t left = 0;
-          if (m > 0.f) {
-            uint32_t hit = 0;
+        for (int g = 0; g < 4; ++g)
+          q[g] = fmaxf(fmaxf(fmaxf(d[8 * g], d[8 * g + 1]), fmaxf(d[8 * g + 2], d[8 * g + 3])),
+                       fmaxf(fmaxf(d[8 * g + 4], d[8 * g + 5]), fmaxf(d[8 * g + 6], d[8 * g + 7])));
+        const float m = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3]));
+        uint32_t left = 0;
+        if (m > 0.f) {
+          // rare per thread, but with 1024 scores per warp and chunk some lane is here about every other chunk: keep it
+          // short — only the 8-column groups that hold a hit are looked at
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(v[j]) > th[j]) ? (1u << j) : 0u;
-            hit &= only;
+          for (int g = 0; g < 4; ++g) {
+            if (q[g] > 0.f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (hit & (1u << j)) {
-                const int col = c * 32 + j;
-                const int at  = atomicAdd(&sCnt[col], 1);
-                if (at < cap) sCand[col * cap + at] = make_uint2(v[j], pos);
-                else left |= 1u << j;
+              for (int e = 0; e < 8; ++e) {
+                const int j = 8 * g + e;
+                if (d[j] > 0.f && ((only >> j) & 1u)) {
+                  const int col = c * 32 + j;
+                  const int at  = atomicAdd(&sCnt[col], 1);
+                  if (at < cap) sCand[col * cap + at] = (static_cast<unsigned long long>(okey(v[j])) << 32) | (~pos);
+                  else left |= 1u << j;
+                }
               }
             }
           }
-          return left;
-        };
+        }
+        return left;
+      };
+      constexpr int TB = L::tb;
+      const bool has_chunks = NCH >= 2 || half == 0;
+      // rounds of TB tiles: all their accumulators are filtered, then ONE barrier decides whether any buffer overflowed
+      for (uint32_t t0 = 0; t0 < item.n_tiles; t0 += TB) {
+        const int nb = static_cast<int>(min(static_cast<uint32_t>(TB), item.n_tiles - t0));
+        uint32_t pend[TB][MYCH];
         bool any_left = false;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          pend[c] = do_chunk(c, 0xffffffffu);
-          any_left |= pend[c] != 0;
+        for (int b = 0; b < TB; ++b) {
+          if (b < nb) {
+            const uint32_t ab = (acc + b) % L::acc, pb = aph ^ ((acc + b) >= static_cast<uint32_t>(L::acc) ? 1u : 0u);
+            wait_dbg(P.dbg, &t_full[ab], pb, 0x402, static_cast<uint32_t>(it), t0 + b);
+            ptx::tc_fence_after_sync();
+#pragma unroll
+            for (int i = 0; i < MYCH; ++i) {
+              const int c = NCH >= 2 ? 2 * i + half : 0;
+              pend[b][i]  = (P.dbg_mode == 2 || !has_chunks) ? 0u : do_chunk(t_lane + ab * NQ, item.b_row0 + (t0 + b) * 128 + row, c, 0xffffffffu);
+              any_left |= pend[b][i] != 0;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < MYCH; ++i) pend[b][i] = 0u;
+          }
         }
         __syncwarp();
+        mark(0x11 + (t0 << 8));
+        uint32_t rounds = 0;
         while (bar_red_or(1, kEpiThreads, any_left)) {
+          if (P.dbg != nullptr && ++rounds > 4096u) {  // an overflow loop that does not converge: report + trap
+            if (lane == 0 && atomicCAS(P.dbg + blockIdx.x * 16, 0u, 0x4ffu) == 0u) { P.dbg[blockIdx.x * 16 + 2] = static_cast<uint32_t>(it); P.dbg[blockIdx.x * 16 + 3] = t0; }
+            __threadfence_system();
+            __trap();
+          }
           for (int col = ew; col < NQ; col += kEpiWarps)
             if (sCnt[col] > cap) compact(col);  // (warp-uniform: every lane reads the same counter)
           ptx::named_bar_sync(1, kEpiThreads);
           any_left = false;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (pend[c]) pend[c] = do_chunk(c, pend[c]);  // re-read from TMEM, re-test against the tightened thresholds
-            any_left |= pend[c] != 0;
+          for (int b = 0; b < TB; ++b) {
+            const uint32_t ab = (acc + b) % L::acc;
+#pragma unroll
+            for (int i = 0; i < MYCH; ++i) {
+              const int c = NCH >= 2 ? 2 * i + half : 0;
+              // re-read from TMEM, re-test against the tightened thresholds.  tcgen05.ld / wait::ld are .sync.aligned: the
+              // whole warp executes them together (lanes with nothing pending pass only = 0)
+              if (__any_sync(0xffffffffu, pend[b][i] != 0)) pend[b][i] = do_chunk(t_lane + ab * NQ, item.b_row0 + (t0 + b) * 128 + row, c, pend[b][i]);
+              any_left |= pend[b][i] != 0;
+            }
           }
           __syncwarp();
         }
+        mark(0x16 + (t0 << 8));
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-        if (++acc == kAcc) { acc = 0; aph ^= 1; }
+        if (lane == 0) {
+          for (int b = 0; b < nb; ++b) ptx::mbar_arrive(&t_empty[(acc + b) % L::acc]);
+        }
+        acc += nb;
+        if (acc >= static_cast<uint32_t>(L::acc)) { acc -= L::acc; aph ^= 1; }
       }
 
       // item done: every column's KC best -> global; publish the query's k-th best for the other items of the same query
       for (int col = ew; col < static_cast<int>(min(item.valid_rows, static_cast<uint32_t>(NQ))); col += kEpiWarps) {
-        unsigned long long mine;
-        const int nk = select_best(col, mine);
-        const uint32_t tb = okey_inv(static_cast<uint32_t>(mine >> 32));
-        const float s_kth = -__uint_as_float(__shfl_sync(0xffffffffu, tb, kth - 1));
+        unsigned long long k0, k1;
+        int r0, r1;
+        const int n  = rank_select(col, k0, k1, r0, r1);
+        const int nk = min(n, KC);
         const uint32_t arow = item.a_row0 + col;
-        if (lane == 0 && P.b_keys != nullptr && nk >= kth) {
-          const float pub = __fmaf_rn(P.b_scale, s_kth, P.b_add ? P.b_add[arow] : 0.f);
-          const int kp    = __float_as_int(pub);
-          atomicMin(P.b_keys + (P.b_idx ? P.b_idx[arow] : arow), kp >= 0 ? kp : kp ^ 0x7fffffff);
-        }
-        if (lane < KC && P.out_score != nullptr) {
-          const int64_t o = static_cast<int64_t>(item.out_off) + static_cast<int64_t>(col) * P.out_row_stride + lane;
-          P.out_score[o]  = lane < nk ? -__uint_as_float(tb) : INFINITY;
-          P.out_pos[o]    = lane < nk ? ~static_cast<uint32_t>(mine) : 0xffffffffu;
-        }
+        const int64_t o     = static_cast<int64_t>(item.out_off) + static_cast<int64_t>(col) * P.out_row_stride;
+        auto emit = [&](unsigned long long key, int r) {
+          if (key == 0ull || r >= KC) return;
+          const float t = __uint_as_float(okey_inv(static_cast<uint32_t>(key >> 32)));
+          if (P.out_score != nullptr) { P.out_score[o + r] = -t; P.out_pos[o + r] = ~static_cast<uint32_t>(key); }
+          if (r == kth - 1 && P.b_keys != nullptr) {  // (n >= kth holds when such a rank exists)
+            const float pub = __fmaf_rn(P.b_scale, -t, P.b_add ? P.b_add[arow] : 0.f);
+            const int kp    = __float_as_int(pub);
+            atomicMin(P.b_keys + (P.b_idx ? P.b_idx[arow] : arow), kp >= 0 ? kp : kp ^ 0x7fffffff);
+          }
+        };
+        emit(k0, r0);
+        emit(k1, r1);
+        if (P.out_score != nullptr && lane >= nk && lane < KC) { P.out_score[o + lane] = INFINITY; P.out_pos[o + lane] = 0xffffffffu; }
       }
       ptx::named_bar_sync(1, kEpiThreads);  // the next item's column init must not overtake another warp's read-out
     }
@@ -528,6 +613,26 @@ pq_stream_build_kernel(const uint8_t* __restrict__ codes, const int64_t* __restr
     reinterpret_cast<uint4*>(out)[o] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   reinterpret_cast<float*>(out + 128 * pq_dim)[r] = ids[row] == pad_id ? INFINITY : (ip ? 0.f : 0.5f * nrm);
+}
+
+// inverse of pq_stream_build_kernel: one CTA per tile, stream block -> codes [128, pq_dim] one code per byte
+__global__ void __launch_bounds__(128) pq_stream_to_flat_kernel(const uint8_t* __restrict__ stream, int pq_dim, uint8_t* __restrict__ codes)
+{
+  __shared__ __align__(16) uint8_t sc[128 * 64];
+  const int64_t tile = blockIdx.x;
+  const int64_t blk  = 128 * static_cast<int64_t>(pq_dim) + 512;
+  const uint8_t* in  = stream + tile * blk;
+  const int nh       = pq_dim / 32;
+  for (int o = threadIdx.x; o < 8 * nh * 32; o += blockDim.x) {
+    const int g = o / (nh * 32), h = (o / 32) % nh, l = o % 32;
+    const uint4 w = reinterpret_cast<const uint4*>(in)[o];
+    const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sc[(16 * g + i) * pq_dim + 32 * h + l] = static_cast<uint8_t>((w4[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+  }
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(codes + tile * 128 * pq_dim);
+  for (int o = threadIdx.x; o < 128 * pq_dim / 16; o += blockDim.x) out[o] = reinterpret_cast<const uint4*>(sc)[o];
 }
 
 __global__ void pq_cb_words_kernel(const float* __restrict__ pq_centers, int pq_dim, uint32_t* __restrict__ words)
@@ -586,19 +691,51 @@ void launch(cudaStream_t stream, int sms, const CUtensorMap& mq_hi, const CUtens
 {
   using L   = layout<NQ, NKB, PASSES>;
   auto kern = pq_stream_scan_kernel<NQ, NKB, PASSES>;
-  a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 48) : 64;
+  a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 64) : 64;  // free slots between compactions: cap - KC
   const int fixed = L::off_cand + NQ * a.cap * 8 + 1024 /*alignment slack of the dynamic segment*/;
   a.cstages = std::min(kMaxCStages, (kSmemLimit - fixed) / a.blk);
   const int forced = env_int("CUVS_B200_PQ_CSTAGES", 0);  // limiter experiments only
   if (forced > 0) a.cstages = std::min(a.cstages, forced);
   B2_EXPECTS(a.cstages >= 2, "pq_stream_scan: shared memory budget exceeded (NQ=%d KC=%d passes=%d)", NQ, a.KC, PASSES);
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.cstages) * a.blk;
+  static uint32_t* dbg_host = nullptr;  // CUVS_B200_PQ_DEBUG=1: deadlock report (see wait_dbg)
+  if (env_int("CUVS_B200_PQ_DEBUG", 0)) {
+    if (!dbg_host) B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&dbg_host), 16 * sizeof(uint32_t) * 1024, cudaHostAllocMapped));
+    memset(dbg_host, 0, 16 * sizeof(uint32_t) * 1024);
+    uint32_t* dptr = nullptr;
+    B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), dbg_host, 0));
+    a.dbg = dptr;
+    a.dbg_mode = env_int("CUVS_B200_PQ_DEBUG", 0);
+    fprintf(stderr, "[pq_stream_scan] NQ=%d NKB=%d PASSES=%d KC=%d cap=%d cstages=%d blk=%d smem=%zu items<=%d\n", NQ, NKB, PASSES, a.KC, a.cap,
+            a.cstages, a.blk, smem, n_items);
+  }
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = n_items < sms ? n_items : sms;
   timed_section ts("pq_stream_scan", stream);
   count_launch();
   kern<<<grid, kThreads, smem, stream>>>(mq_hi, mq_lo, a);
   B2_CUDA(cudaGetLastError());
+  if (a.dbg != nullptr) {
+    cudaError_t e = cudaErrorNotReady;
+    for (int i = 0; i < 80 && e == cudaErrorNotReady; ++i) {  // poll for ~8 s: a hang must not block the host forever
+      e = cudaStreamQuery(stream);
+      if (e == cudaErrorNotReady) usleep(100000);
+    }
+    int shown = 0;
+    for (int b = 0; b < grid && b < 1024 && shown < 6; ++b)
+      if (dbg_host[b * 16] || e != cudaSuccess) {
+        ++shown;
+        fprintf(stderr, "[pq_stream_scan] CTA %d: stuck wait 0x%x parity %u a=%u b=%u warp %u | epilogue stages %x %x %x %x\n", b, dbg_host[b * 16],
+                dbg_host[b * 16 + 1], dbg_host[b * 16 + 2], dbg_host[b * 16 + 3], dbg_host[b * 16 + 4], dbg_host[b * 16 + 8], dbg_host[b * 16 + 9],
+                dbg_host[b * 16 + 10], dbg_host[b * 16 + 11]);
+      }
+    if (e == cudaErrorNotReady) {
+      fprintf(stderr, "[pq_stream_scan] kernel still running after 8 s: giving up (process exits)\n");
+      fflush(stderr);
+      _exit(3);
+    }
+    B2_EXPECTS(e == cudaSuccess, "pq_stream_scan (debug): kernel failed: %s", cudaGetErrorString(e));
+  }
 }
 
 }  // namespace
@@ -621,6 +758,15 @@ void pq_stream_build(cudaStream_t s, const uint8_t* codes, const int64_t* ids, i
     count_launch();
     pq_stream_build_kernel<<<static_cast<unsigned>(rows_total / 128), 128, 0, s>>>(codes, ids, pad_id, pq_dim, pq_centers, ip, stream);
   }
+  B2_CUDA(cudaGetLastError());
+}
+
+void pq_stream_to_flat(cudaStream_t s, const uint8_t* stream, int64_t rows_total, int pq_dim, uint8_t* codes)
+{
+  B2_EXPECTS(pq_dim == 32 || pq_dim == 64, "pq_stream_to_flat: pq_dim must be 32 or 64");
+  if (rows_total == 0) return;
+  count_launch();
+  pq_stream_to_flat_kernel<<<static_cast<unsigned>(rows_total / 128), 128, 0, s>>>(stream, pq_dim, codes);
   B2_CUDA(cudaGetLastError());
 }
 

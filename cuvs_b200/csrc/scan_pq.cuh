@@ -40,6 +40,9 @@ bool pq_stream_supported(int device, int pq_dim, int pq_len, int pq_bits, bool p
 void pq_stream_build(cudaStream_t s, const uint8_t* codes, const int64_t* ids, int64_t pad_id, int64_t rows_total, int pq_dim,
                      const float* pq_centers, bool ip, uint8_t* stream, uint32_t* cb_words);
 
+/** The flat form back from the stream: codes [rows_total, pq_dim], one code per byte (getters, extend, serialize, LUT path). */
+void pq_stream_to_flat(cudaStream_t s, const uint8_t* stream, int64_t rows_total, int pq_dim, uint8_t* codes);
+
 /** Queries per work item the scan wants for an average of `pairs_per_list` probing queries per list (32, 64 or 128). */
 int pq_stream_group(double pairs_per_list, int KC, int passes);
 

@@ -33,7 +33,7 @@ class Index:
 @auto_sync_resources
 def build(dataset, metric="sqeuclidean", metric_arg=2.0, resources=None):
     ds = as_tensor(dataset)
-    if ds.dtype not in (torch.float32,):
+    if ds.dtype not in (torch.float32, torch.float16, torch.int8, torch.uint8):
         raise TypeError("dtype %s not supported" % ds.dtype)
     idx = Index()
     dl = DL(ds)
@@ -48,7 +48,7 @@ def search(index, queries, k, neighbors=None, distances=None, resources=None, pr
     if not index.trained:
         raise ValueError("Index needs to be built before calling search.")
     q = as_tensor(queries)
-    if q.dtype != torch.float32:
+    if q.dtype not in (torch.float32, torch.float16, torch.int8, torch.uint8):
         raise TypeError("dtype %s not supported" % q.dtype)
     nq = q.shape[0]
     if neighbors is None:

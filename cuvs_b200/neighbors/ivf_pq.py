@@ -150,7 +150,7 @@ class Index:
 @auto_sync_resources
 def build(index_params, dataset, resources=None):
     ds = as_tensor(dataset)
-    if ds.dtype != torch.float32:
+    if ds.dtype not in (torch.float32, torch.float16, torch.int8, torch.uint8):
         raise TypeError("dtype %s not supported" % ds.dtype)
     idx = Index()
     check(lib.cuvsIvfPqBuild(resources.get_c_obj(), index_params._p, DL(ds).ptr, idx._p))

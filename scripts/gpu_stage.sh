@@ -9,6 +9,11 @@ for stage in "$@"; do
     c2)         timeout 600 python bench.py --workload ivf_pq_c2 --steps 10 --no-cpu --no-aux > gpurun_out/bench_c2.log 2>&1; echo "c2 rc=$?" ;;
     sweep100m)  timeout 900 python scripts/sweep_probes.py 100000000 16384 "32,40,48,56,64" > gpurun_out/sweep100m.log 2>&1; echo "sweep rc=$?" ;;
     bench)      timeout 1500 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?" ;;
+    onec2)      timeout 600 python scripts/sweep_probes.py 10000000 1024 "64" > gpurun_out/onec2.log 2>&1; echo "onec2 rc=$?" ;;
+    one100m)    timeout 900 python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/one100m.log 2>&1; echo "one100m rc=$?" ;;
+    prof100m)   CUVS_B200_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:pq_stream_scan -c 1 -f -o gpurun_out/r02_pq100m python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/prof100m.log 2>&1; echo "prof100m rc=$?" ;;
+    launches100m) CUVS_B200_PROFILE=1 timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches100m.csv python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/launches100m.log 2>&1; echo "launches100m rc=$?" ;;
+    profc2)     CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:pq_stream_scan -c 1 -f -o gpurun_out/r02_pqc2 python scripts/sweep_probes.py 10000000 1024 "64" > gpurun_out/profc2.log 2>&1; echo "profc2 rc=$?" ;;
     smoke)      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     *)          echo "unknown stage $stage" ;;
   esac

@@ -132,3 +132,30 @@ def test_plain_c_client_compiles_links_and_runs_without_a_gpu(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe), "--version"], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("libcuvs_c 26."), out.stdout + out.stderr
+
+
+def _build_cpp_client(out):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", os.path.join(root, "examples", "cpp", "ivf_pq_search.cpp"),
+           "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include", "-L" + os.path.join(root, "cuvs_b200", "lib"), "-lcuvs_c",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(root, "cuvs_b200", "lib"), "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_cpp_header_adaptor_compiles_links_and_runs_without_a_gpu(tmp_path):
+    """include/cuvs_b200/cuvs.hpp: the reference's C++ call shape (cuvs::neighbors::ivf_pq::build/search over mdspan-like
+    views, ivf_pq.hpp:1821-1828) as header-only templates over the C ABI; the example client compiles with -Wall -Werror,
+    links the in-tree library and runs its GPU-free path."""
+    exe = tmp_path / "cpp_client"
+    _build_cpp_client(exe)
+    out = subprocess.run([str(exe), "--no-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("libcuvs_c 26."), out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_header_adaptor_search_on_the_gpu(tmp_path):
+    exe = tmp_path / "cpp_client"
+    _build_cpp_client(exe)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "CPP_ADAPTOR_OK" in out.stdout, out.stdout + out.stderr
