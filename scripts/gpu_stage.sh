@@ -4,8 +4,8 @@
 mkdir -p gpurun_out
 for stage in "$@"; do
   case "$stage" in
-    pq_tests)   timeout 900 python -m pytest tests/test_ivf_pq_gpu.py -x -q > gpurun_out/pq_tests.log 2>&1; echo "pq_tests rc=$?" ;;
-    all_tests)  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/all_tests.log 2>&1; echo "all_tests rc=$?" ;;
+    pq_tests)   timeout 900 python -m pytest tests/test_ivf_pq_gpu.py -q > gpurun_out/pq_tests.log 2>&1; echo "pq_tests rc=$?" ;;
+    all_tests)  timeout 1700 python -m pytest tests -m gpu -q > gpurun_out/all_tests.log 2>&1; echo "all_tests rc=$?" ;;
     c2)         timeout 600 python bench.py --workload ivf_pq_c2 --steps 10 --no-cpu --no-aux > gpurun_out/bench_c2.log 2>&1; echo "c2 rc=$?" ;;
     sweep100m)  timeout 900 python scripts/sweep_probes.py 100000000 16384 "32,40,48,56,64" > gpurun_out/sweep100m.log 2>&1; echo "sweep rc=$?" ;;
     bench)      timeout 1500 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?" ;;

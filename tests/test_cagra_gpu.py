@@ -162,7 +162,7 @@ def test_fp16_walk_reranks_with_fp32_rows():
     assert torch.equal(i_again, i32) and torch.equal(d_again, d32)
 
 
-@pytest.mark.parametrize("nq,itopk,k", [(1, 64, 10), (16, 64, 10), (64, 128, 10), (128, 256, 32), (40, 32, 5)])
+@pytest.mark.parametrize("nq,itopk,k", [(1, 64, 10), (16, 64, 10), (64, 128, 10), (128, 128, 32), (40, 32, 5)])
 def test_multi_cta_walk_small_batches(nq, itopk, k):
     """a17: the MULTI_CTA algorithm (search_multi_cta_jit.cuh:56-363) — max(search_width, itopk/32) walkers per query with
     32-entry lists, parents claimed through a shared traversed table, lists merged + de-duplicated.  Small batches are what

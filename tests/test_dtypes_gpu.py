@@ -27,8 +27,9 @@ def test_brute_force_narrow_dtypes_match_the_oracle_on_the_widened_values(dtype)
     d, i = brute_force.search(index, torch.from_numpy(qs).cuda(), 10)
     rd, ri = oracle.knn(ds.astype(np.float32), qs.astype(np.float32), 10)
     assert (i.cpu().numpy() == ri).all() and (d.cpu().numpy() == rd).all()
-    with pytest.raises(Exception):
-        brute_force.search(index, torch.from_numpy(qs.astype(np.float32)).cuda(), 10)  # type mismatch between index and queries
+    if dtype != np.float16:  # (the reference compares the DLPack type CODE only: c/src/neighbors/brute_force.cpp:204)
+        with pytest.raises(Exception):
+            brute_force.search(index, torch.from_numpy(qs.astype(np.float32)).cuda(), 10)  # type mismatch between index and queries
 
 
 @pytest.mark.parametrize("dtype", [np.float16, np.int8, np.uint8])
@@ -43,7 +44,9 @@ def test_ivf_indexes_narrow_dtypes(dtype):
     d, i = ivf_pq.search(ivf_pq.SearchParams(n_probes=32), pq, torch.from_numpy(qs).cuda(), 10)
     f32 = ivf_pq.build(ivf_pq.IndexParams(n_lists=32, pq_dim=32, kmeans_n_iters=5), torch.from_numpy(ds.astype(np.float32)).cuda())
     d2, i2 = ivf_pq.search(ivf_pq.SearchParams(n_probes=32), f32, torch.from_numpy(qs.astype(np.float32)).cuda(), 10)
-    assert torch.equal(i, i2) and torch.equal(d, d2)   # same values in, same index, same answers
+    # same values in -> the same quality out (the k-means build uses atomics, so two builds are not bit-identical)
+    r_narrow, r_f32 = oracle.recall(i.cpu().numpy(), gi), oracle.recall(i2.cpu().numpy(), gi)
+    assert abs(r_narrow - r_f32) <= 0.03 and r_narrow >= 0.5, (r_narrow, r_f32)
 
 
 @pytest.mark.parametrize("dtype", [np.float16, np.uint8])

@@ -44,8 +44,9 @@ def test_multi_gpu_ivf_flat_matches_exact_knn(mode):
     t_ds, t_q = torch.from_numpy(ds), torch.from_numpy(qs)
     nb = torch.empty((300, 10), dtype=torch.int64)
     dd = torch.empty((300, 10), dtype=torch.float32)
-    check(lib.cuvsMultiGpuIvfFlatBuild(res, ip, DL(t_ds).ptr, index))
-    check(lib.cuvsMultiGpuIvfFlatSearch(res, sp, index, DL(t_q).ptr, DL(nb).ptr, DL(dd).ptr))
+    d_ds, d_q, d_nb, d_dd = DL(t_ds), DL(t_q), DL(nb), DL(dd)
+    check(lib.cuvsMultiGpuIvfFlatBuild(res, ip, d_ds.ptr, index))
+    check(lib.cuvsMultiGpuIvfFlatSearch(res, sp, index, d_q.ptr, d_nb.ptr, d_dd.ptr))
     gd, gi = oracle.knn(ds, qs, 10)
     assert oracle.recall_with_ties(nb.numpy(), dd.numpy(), gi, gd, eps=1e-4) >= 0.999
     assert (nb.numpy() == gi).mean() >= 0.995
@@ -64,8 +65,9 @@ def test_pairwise_distance(metric, code):
     y = uniform(129, 70, 2, -1, 1)
     out = torch.empty((257, 129), dtype=torch.float32, device="cuda")
     res = Resources()
-    check(lib.cuvsPairwiseDistance(res.get_c_obj(), DL(torch.from_numpy(x).cuda()).ptr, DL(torch.from_numpy(y).cuda()).ptr, DL(out).ptr,
-                                   C.c_int(code), C.c_float(2.0)))
+    xg, yg = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    dx, dy, do = DL(xg), DL(yg), DL(out)  # (held: a DL owns the shape array the DLTensor points at)
+    check(lib.cuvsPairwiseDistance(res.get_c_obj(), dx.ptr, dy.ptr, do.ptr, C.c_int(code), C.c_float(2.0)))
     res.sync()
     x64, y64 = x.astype(np.float64), y.astype(np.float64)
     dot = x64 @ y64.T
@@ -87,7 +89,8 @@ def test_allgather_merge_world_of_one():
     d = torch.sort(torch.rand((500, 10), device="cuda"), dim=1).values
     i = torch.randint(0, 1 << 40, (500, 10), device="cuda")
     od, oi = torch.empty_like(d), torch.empty_like(i)
-    check(lib.cuvsB200AllGatherMergeTopK(res.get_c_obj(), comm, DL(d).ptr, DL(i).ptr, DL(od).ptr, DL(oi).ptr, C.c_bool(True)))
+    h = [DL(d), DL(i), DL(od), DL(oi)]
+    check(lib.cuvsB200AllGatherMergeTopK(res.get_c_obj(), comm, h[0].ptr, h[1].ptr, h[2].ptr, h[3].ptr, C.c_bool(True)))
     res.sync()
     assert torch.equal(od, d) and torch.equal(oi, i)
     check(lib.cuvsB200CommDestroy(comm))
