@@ -352,7 +352,7 @@ cuvsError_t cuvsMatrixSliceRows(cuvsResources_t, DLManagedTensor* src_m, int64_t
     dst.dtype       = src.dtype;
     dst.device      = src.device;
     dst.ndim        = src.ndim;
-    dst.byte_offset = src.byte_offset;
+    dst.byte_offset = 0;
     dst.shape       = new int64_t[dst.ndim];
     dst.shape[0]    = end - start;
     dst.strides     = nullptr;

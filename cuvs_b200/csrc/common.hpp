@@ -181,10 +181,14 @@ inline bool dl_is_f_contiguous(const DLTensor& t)
   }
   return true;
 }
+// `byte_offset` is deliberately NOT applied: the reference's C layer never reads it (from_dlpack builds the mdspan from
+// `tensor.data` alone: c/src/core/detail/interop.hpp:138) and its own C tests pass stack DLManagedTensors that leave the field
+// uninitialised (c/tests/neighbors/run_brute_force_c.c:26-36) — honouring it would turn those callers' garbage into
+// misaligned device addresses.  Producers that need an offset fold it into `data` (torch's DLPack exporter does).
 template <typename T>
 inline T* dl_ptr(const DLTensor& t)
 {
-  return reinterpret_cast<T*>(static_cast<char*>(t.data) + t.byte_offset);
+  return reinterpret_cast<T*>(t.data);
 }
 inline const DLTensor& dl_req(DLManagedTensor* m, const char* name)
 {
@@ -208,7 +212,7 @@ struct dl_row_slice {
     shape[1]    = src.shape[1];
     t.shape     = shape;
     t.strides   = nullptr;
-    t.data      = static_cast<char*>(src.data) + src.byte_offset + r0 * src.shape[1] * ((src.dtype.bits * src.dtype.lanes + 7) / 8);
+    t.data      = static_cast<char*>(src.data) + r0 * src.shape[1] * ((src.dtype.bits * src.dtype.lanes + 7) / 8);
     t.byte_offset = 0;
   }
   dl_row_slice(const dl_row_slice&) = delete;

@@ -14,6 +14,7 @@
 #include <cuvs/selection/select_k.h>
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace b200 {
 namespace {
@@ -193,10 +194,160 @@ __global__ void __launch_bounds__(1024) select_k_kernel(const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Medium rows (2k..32k elements, k <= 256: the coarse search's n_lists distances per query).  The radix kernel above reads
+// the row six times and its first two 8-bit passes are wasted on distances (one exponent => one bucket).  Here the row is
+// read ONCE into registers as composite keys K = key << 32 | position (unique, so "smaller position wins" is part of the
+// order); the keys in play are binned LINEARLY over their actual [min, max] span into 2048 buckets, the bucket holding the
+// k-th key is found by one warp, everything below it is a winner, and the bucket itself (a handful of keys) is finished by
+// rank counting — or, if it is crowded (ties, clustered values), becomes the next span.  One global read, ~3 register passes.
+constexpr int kRegThreads = 512;
+constexpr int kRegBins    = 2048;
+constexpr int kRegEqCap   = 1024;
+constexpr int kRegMaxK    = 256;
+
+template <int E, typename IdxIn, typename IdxOut, bool HasIdx>
+__global__ void __launch_bounds__(kRegThreads) select_k_reg_kernel(const float* __restrict__ in_val, const IdxIn* __restrict__ in_idx,
+                                                                   int64_t len, int64_t in_ld, int k, float* __restrict__ out_val,
+                                                                   IdxOut* __restrict__ out_idx, bool select_min)
+{
+  __shared__ uint32_t hist[kRegBins];
+  __shared__ unsigned long long okeys[kRegMaxK];
+  __shared__ unsigned long long ebuf[kRegEqCap];
+  __shared__ unsigned long long red[2 * (kRegThreads / 32)];
+  __shared__ uint32_t scal[8];  // [0] threshold bucket [1] keys below it [2] keys in it [3] winners stored [4] bucket keys stored
+
+  const int64_t row = blockIdx.x;
+  const float* v    = in_val + row * in_ld;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int k_eff = len < k ? static_cast<int>(len) : k;
+
+  uint32_t u[E];
+  unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const int64_t i = static_cast<int64_t>(j) * kRegThreads + tid;
+    u[j] = 0u;
+    if (i < len) {
+      u[j] = f2key(v[i], select_min);
+      const unsigned long long K = (static_cast<unsigned long long>(u[j]) << 32) | static_cast<uint32_t>(i);
+      mn = K < mn ? K : mn;
+      mx = K > mx ? K : mx;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+  }
+  if (lane == 0) { red[wid] = mn; red[kRegThreads / 32 + wid] = mx; }
+  if (tid == 0) { scal[3] = 0; scal[4] = 0; }
+  __syncthreads();
+  unsigned long long lo = red[0], hi = red[kRegThreads / 32];
+#pragma unroll
+  for (int w = 1; w < kRegThreads / 32; ++w) {
+    lo = red[w] < lo ? red[w] : lo;
+    hi = red[kRegThreads / 32 + w] > hi ? red[kRegThreads / 32 + w] : hi;
+  }
+  unsigned long long span = hi - lo;  // keys in play: lo <= K <= lo + span
+  uint32_t need = static_cast<uint32_t>(k_eff);
+
+  while (need > 0) {
+    const int s = span >= static_cast<unsigned long long>(kRegBins) ? (64 - __clzll(static_cast<long long>(span))) - 11 : 0;  // (span >> s) < 2048
+    for (int i = tid; i < kRegBins; i += kRegThreads) hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int64_t i = static_cast<int64_t>(j) * kRegThreads + tid;
+      const unsigned long long K = (static_cast<unsigned long long>(u[j]) << 32) | static_cast<uint32_t>(i);
+      if (i < len && K >= lo && K - lo <= span) atomicAdd(&hist[static_cast<uint32_t>((K - lo) >> s)], 1u);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t sum = 0;
+      for (int b = 0; b < kRegBins / 32; ++b) sum += hist[lane * (kRegBins / 32) + b];
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      uint32_t c = incl - sum;
+      if (c < need && need <= incl) {
+        for (int b = 0; b < kRegBins / 32; ++b) {
+          const uint32_t h = hist[lane * (kRegBins / 32) + b];
+          if (c < need && need <= c + h) { scal[0] = lane * (kRegBins / 32) + b; scal[1] = c; scal[2] = h; }
+          c += h;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t bstar = scal[0], below = scal[1], inb = scal[2];
+    const bool finish = inb <= static_cast<uint32_t>(kRegEqCap);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int64_t i = static_cast<int64_t>(j) * kRegThreads + tid;
+      const unsigned long long K = (static_cast<unsigned long long>(u[j]) << 32) | static_cast<uint32_t>(i);
+      if (i < len && K >= lo && K - lo <= span) {
+        const uint32_t b = static_cast<uint32_t>((K - lo) >> s);
+        if (b < bstar) okeys[atomicAdd(&scal[3], 1u)] = K;
+        else if (b == bstar && finish) ebuf[atomicAdd(&scal[4], 1u)] = K;
+      }
+    }
+    need -= below;
+    __syncthreads();
+    if (finish) {
+      // the bucket's `need` smallest keys, by rank counting (keys are unique)
+      const uint32_t base = scal[3];
+      for (uint32_t e = tid; e < inb; e += kRegThreads) {
+        const unsigned long long K = ebuf[e];
+        uint32_t r = 0;
+        for (uint32_t o = 0; o < inb; ++o) r += ebuf[o] < K ? 1u : 0u;
+        if (r < need) okeys[base + r] = K;
+      }
+      need = 0;
+    } else {
+      lo += static_cast<unsigned long long>(bstar) << s;  // (s > 0 here: with s == 0 a bucket holds one key)
+      span = (1ull << s) - 1ull;
+    }
+    __syncthreads();
+  }
+
+  // ascending (key, position): rank counting among the k winners
+  for (int t = tid; t < k; t += kRegThreads) {
+    if (t < k_eff) {
+      const unsigned long long K = okeys[t];
+      int r = 0;
+      for (int o = 0; o < k_eff; ++o) r += okeys[o] < K ? 1 : 0;
+      const uint32_t pos = static_cast<uint32_t>(K);
+      out_val[row * k + r] = v[pos];
+      if constexpr (HasIdx) out_idx[row * k + r] = static_cast<IdxOut>(in_idx[row * in_ld + pos]);
+      else out_idx[row * k + r] = static_cast<IdxOut>(pos);
+    } else {
+      out_val[row * k + t] = select_min ? FLT_MAX : -FLT_MAX;
+      out_idx[row * k + t] = all_ones<IdxOut>();
+    }
+  }
+}
+
 template <typename IdxIn, typename IdxOut, bool HasIdx>
 void launch(cudaStream_t stream, const float* in_val, const void* in_idx, int64_t batch, int64_t len, int64_t in_ld,
             int k, float* out_val, void* out_idx, bool select_min)
 {
+  if (len >= 2048 && len <= 64 * kRegThreads && k <= kRegMaxK && getenv("CUVS_B200_SELECT_RADIX") == nullptr) {
+    count_launch();
+    const unsigned grid = static_cast<unsigned>(batch);
+    auto ii = static_cast<const IdxIn*>(in_idx);
+    auto oo = static_cast<IdxOut*>(out_idx);
+    if (len <= 8 * kRegThreads) select_k_reg_kernel<8, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
+    else if (len <= 16 * kRegThreads) select_k_reg_kernel<16, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
+    else if (len <= 32 * kRegThreads) select_k_reg_kernel<32, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
+    else select_k_reg_kernel<64, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
+    B2_CUDA(cudaGetLastError());
+    return;
+  }
   int kpow2 = 1;
   while (kpow2 < k) kpow2 <<= 1;
   if (kpow2 < 2) kpow2 = 2;

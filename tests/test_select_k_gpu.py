@@ -37,6 +37,37 @@ def test_select_k_matches_oracle(batch, length, k, select_min):
     np.testing.assert_array_equal(ov, rv)
 
 
+@pytest.mark.parametrize("length,k", [(2048, 48), (4096, 1), (4097, 256), (16384, 48), (20000, 100), (32768, 64), (16384, 300)])
+@pytest.mark.parametrize("kind", ["normal", "narrow", "all_equal", "three_values", "with_inf"])
+def test_select_k_medium_rows_register_path(length, k, kind):
+    """Rows of 2k..32k elements with k <= 256 take the register-resident kernel (linear binning over the live span, crowded
+    buckets re-binned): same answers as the oracle incl. the tie rule, for value distributions that stress the binning."""
+    rng = np.random.default_rng(length + k)
+    batch = 5
+    if kind == "normal":
+        v = rng.standard_normal((batch, length)).astype(np.float32)
+        v[:, ::5] = np.round(v[:, ::5], 1)
+    elif kind == "narrow":          # coarse-search distances: one exponent, tiny spread, many exact ties
+        v = (100.0 + 1e-4 * rng.integers(0, 50, (batch, length))).astype(np.float32)
+    elif kind == "all_equal":
+        v = np.full((batch, length), 3.25, np.float32)
+    elif kind == "three_values":
+        v = rng.choice(np.array([-1.0, 0.0, 7.5], np.float32), (batch, length))
+    else:
+        v = rng.standard_normal((batch, length)).astype(np.float32)
+        v[:, ::3] = np.inf
+        v[:, 1::97] = -np.inf
+    for select_min in (True, False):
+        ov, oi = _select(v, k, select_min)
+        rv, ri = oracle.select_k(v, k, select_min)
+        np.testing.assert_array_equal(oi, ri)
+        np.testing.assert_array_equal(ov, rv)
+    idx = rng.permutation(batch * length).astype(np.int64).reshape(batch, length)
+    ov, oi = _select(v, min(k, 64), True, idx)
+    rv, ri = oracle.select_k(v, min(k, 64), True, idx)
+    np.testing.assert_array_equal(oi, ri)
+
+
 def test_select_k_with_payload_and_special_values():
     v = np.array([[np.inf, -np.inf, 0.0, -0.0, 5.0, 5.0, 1e-38, 3.4e38]], np.float32)
     idx = (np.arange(8, dtype=np.int64) * 10 + 3)[None, :]
