@@ -179,6 +179,77 @@ __device__ __noinline__ uint32_t pq_filter_chunk(uint32_t taddr, uint32_t pos, c
   return left;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3 (sm_100): NaN operands are ignored like fmaxf
+  return r;
+}
+
+// One 32-column chunk of up to four tiles of an epilogue round: the chunk's 32 thresholds are loaded ONCE (they were 16 % of the
+// kernel's shared-memory wavefronts when re-read per tile) and stay in registers while the tiles' accumulators stream through.
+// taddr = TMEM address of the chunk in accumulator buffer 0; tile b of the round sits in buffer (buf0 + b) % nacc (nq columns
+// per buffer) and is waited for here (t_full, parity aph, flipped where the buffer index wraps); mask = tiles of the round this
+// warp owns (warp-uniform: tcgen05.ld is .sync.aligned).  Returns, per tile, the columns whose candidate could not be stored.
+__device__ __noinline__ uint4 pq_filter_round(uint32_t taddr, uint32_t buf0, uint32_t nacc, uint32_t nq, uint32_t mask, uint32_t pos0,
+                                              const float* __restrict__ thr, int* cnt, unsigned long long* cand, int cap,
+                                              uint64_t* t_full, uint32_t aph)
+{
+  float th[32];
+  {
+    const float4* th4 = reinterpret_cast<const float4*>(thr);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 x = th4[j4];
+      th[4 * j4] = x.x; th[4 * j4 + 1] = x.y; th[4 * j4 + 2] = x.z; th[4 * j4 + 3] = x.w;
+    }
+  }
+  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+#pragma unroll 1
+  for (uint32_t b = 0; b < 4; ++b) {
+    if (!((mask >> b) & 1u)) continue;
+    uint32_t ab = buf0 + b, par = aph;
+    if (ab >= nacc) { ab -= nacc; par ^= 1u; }
+    ptx::mbar_wait(&t_full[ab], par);
+    ptx::tc_fence_after_sync();
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + ab * nq, v);
+    ptx::tmem_ld_wait();
+    float q[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float m = fmax3(__uint_as_float(v[8 * g]) - th[8 * g], __uint_as_float(v[8 * g + 1]) - th[8 * g + 1], __uint_as_float(v[8 * g + 2]) - th[8 * g + 2]);
+      m       = fmax3(m, __uint_as_float(v[8 * g + 3]) - th[8 * g + 3], __uint_as_float(v[8 * g + 4]) - th[8 * g + 4]);
+      m       = fmax3(m, __uint_as_float(v[8 * g + 5]) - th[8 * g + 5], __uint_as_float(v[8 * g + 6]) - th[8 * g + 6]);
+      q[g]    = fmaxf(m, __uint_as_float(v[8 * g + 7]) - th[8 * g + 7]);
+    }
+    uint32_t lf = 0;
+    if (fmaxf(fmax3(q[0], q[1], q[2]), q[3]) > 0.f) {
+      const uint32_t pos = pos0 + b * 128u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (q[g] > 0.f) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * g + e;
+            if (__uint_as_float(v[j]) - th[j] > 0.f) {
+              const int at = atomicAdd(&cnt[j], 1);
+              if (at < cap) cand[j * cap + at] = (static_cast<unsigned long long>(okey(v[j])) << 32) | (~pos);
+              else lf |= 1u << j;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (b == 0) l0 = lf;
+    else if (b == 1) l1 = lf;
+    else if (b == 2) l2 = lf;
+    else l3 = lf;
+  }
+  return make_uint4(l0, l1, l2, l3);
+}
+
 // Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l and l + 32 (64-bit keys
 // order(t) << 32 | ~pos, unique, 0 = none); every entry is broadcast from shared memory and each lane counts how many beat its
 // own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + two compare-adds.
@@ -334,7 +405,6 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NQ);
     const uint32_t q_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sQ));
     const uint32_t d_lo0   = ptx::smem_desc_lo(ptx::smem_u32(sDec));
     const uint32_t ones_lo = ptx::smem_desc_lo(ptx::smem_u32(sOnes));
@@ -346,6 +416,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       if (++ss == kSched) { ss = 0; sp ^= 1; }
       if (it < 0) break;
       const uint32_t n_tiles = __shfl_sync(0xffffffffu, P.items[it].n_tiles, 0);
+      // N of the MMA = the item's live queries rounded up to 16: a narrow item neither reads nor multiplies the unused rows
+      const uint32_t n_live = min(static_cast<uint32_t>(NQ), (__shfl_sync(0xffffffffu, P.items[it].valid_rows, 0) + 15u) & ~15u);
+      const uint32_t idesc  = ptx::make_idesc_bf16(128, static_cast<int>(max(n_live, 16u)));
       wait_dbg(P.dbg, q_full, qph, 0x202, static_cast<uint32_t>(it), 0);
       ptx::tc_fence_after_sync();
       for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -426,8 +499,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           for (int i = 0; i < 16; ++i)
             *reinterpret_cast<uint32_t*>(dst + h * kDecTile + (i >> 3) * 1024 + offx[i & 7]) = val[i];
         }
-        if (lane < 16) {
-          // -hn/2 as three bf16 pieces (exact), identical in both 16-byte chunks of the row; +inf (padding) -> -inf
+        {
+          // -hn/2 as three bf16 pieces (exact), identical in both 16-byte chunks of the row; +inf (padding) -> -inf.
+          // Lane l writes chunk l / 16 of row l % 16: 32 distinct 16-byte slots of one 512-byte span (conflict-free)
           const float hh = -0.5f * hn;
           __nv_bfloat16 p0 = __float2bfloat16_rn(hh), p1 = __float2bfloat16_rn(0.f), p2 = p1;
           if (!isinf(hh)) {
@@ -437,9 +511,8 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           }
           const uint32_t w0 = static_cast<uint32_t>(__bfloat16_as_ushort(p0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(p1)) << 16);
           const uint32_t w1 = static_cast<uint32_t>(__bfloat16_as_ushort(p2));
-          uint4* ext = reinterpret_cast<uint4*>(sDec + ds * L::dec_stage + NKB * kDecTile + (16 * dw + lane) * 32);
-          ext[0] = make_uint4(w0, w1, 0u, 0u);
-          ext[1] = make_uint4(w0, w1, 0u, 0u);
+          *reinterpret_cast<uint4*>(sDec + ds * L::dec_stage + NKB * kDecTile + (16 * dw + (lane & 15)) * 32 + (lane >> 4) * 16) =
+            make_uint4(w0, w1, 0u, 0u);
         }
         // every loaded register (codes of both halves, half-norm) has fed an issued instruction by now: release the slot
         __syncwarp();
@@ -454,14 +527,13 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     // ------------------------------------------------------------------ epilogue: thread = list row, columns = queries
     const int ew      = warp - kEpiWarp0;
     const int quarter = warp & 3;
-    const int half    = ew >> 2;  // this warp takes the chunks c with c % 2 == half (NQ = 32: the second half only joins the barriers)
+    const int half    = ew >> 2;  // which of the lane quarter's two warps: they split the round's (tile, chunk) units
     const int row     = quarter * 32 + lane;
     const int te      = static_cast<int>(threadIdx.x) - 32 * kEpiWarp0;  // 0..127
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int cap = P.cap, KC = P.KC;
     const int kth = (P.kth > 0 && P.kth < KC) ? P.kth : KC;
     constexpr int NCH = NQ / 32;
-    constexpr int MYCH = NCH >= 2 ? NCH / 2 : 1;  // chunks per epilogue warp
     uint32_t acc = 0, aph = 0, ss = 0, sp = 0;
 
     auto rank_select = [&](int col, unsigned long long& k0, unsigned long long& k1, int& r0, int& r1) -> int {
@@ -486,8 +558,12 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       __syncwarp();
     };
 
-    auto mark = [&](uint32_t stage) {
+    auto mark = [&](uint32_t stage) {  // epilogue progress markers for the deadlock report (compiled in with -DCUVS_B200_PQ_MARKS)
+#ifdef CUVS_B200_PQ_MARKS
       if (P.dbg != nullptr && lane == 0) { reinterpret_cast<volatile uint32_t*>(P.dbg)[blockIdx.x * 16 + 8 + ew] = stage; __threadfence_system(); }
+#else
+      (void)stage;
+#endif
     };
     for (;;) {
       wait_dbg(P.dbg, &s_full[ss], sp, 0x401, ss, 0);
@@ -520,38 +596,33 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
         return pq_filter_chunk(taddr + c * 32, pos, sThr + c * 32, sCnt + c * 32, sCand + c * 32 * cap, cap, only);
       };
       constexpr int TB = L::tb;
-      const bool has_chunks = NCH >= 2 || half == 0;
+      static_assert(TB <= 4, "pq_filter_round handles up to four tiles");
+      // Work units of a round = (tile, chunk) for the chunks that hold queries; the two warps of a TMEM lane quarter split them:
+      // by chunk when the item has an even number of live chunks, else in a checkerboard over (tile, chunk) — an item with
+      // <= 32 probing queries (most items of a sparsely probed index) keeps BOTH warps busy on alternating tiles instead of
+      // sending one of them through 32 columns of +inf thresholds.
+      const int nvc = min(NCH, (static_cast<int>(item.valid_rows) + 31) >> 5);
+      auto mine = [&](uint32_t t, int c) -> bool { return (((nvc & 1) ? (t + c) : static_cast<uint32_t>(c)) & 1u) == static_cast<uint32_t>(half); };
       // rounds of TB tiles: all their accumulators are filtered, then ONE barrier decides whether any buffer overflowed
       for (uint32_t t0 = 0; t0 < item.n_tiles; t0 += min(TB, P.tb_limit)) {
         const int nb = static_cast<int>(min(static_cast<uint32_t>(min(TB, P.tb_limit)), item.n_tiles - t0));
-        uint32_t pend[TB][MYCH];
+        uint4 pend[NCH];  // per chunk: .x/.y/.z/.w = columns still pending in tile 0..3 of the round
         bool any_left = false;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) {
-          if (b < nb) {
-            const uint32_t ab = (acc + b) % L::acc, pb = aph ^ ((acc + b) >= static_cast<uint32_t>(L::acc) ? 1u : 0u);
-            wait_dbg(P.dbg, &t_full[ab], pb, 0x402, static_cast<uint32_t>(it), t0 + b);
-            ptx::tc_fence_after_sync();
+        for (int c = 0; c < NCH; ++c) {
+          pend[c] = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t mask = 0;
 #pragma unroll
-            for (int i = 0; i < MYCH; ++i) {
-              const int c = NCH >= 2 ? 2 * i + half : 0;
-              pend[b][i]  = (P.dbg_mode == 2 || !has_chunks) ? 0u : do_chunk(t_lane + ab * NQ, item.b_row0 + (t0 + b) * 128 + row, c, 0xffffffffu);
-              any_left |= pend[b][i] != 0;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < MYCH; ++i) pend[b][i] = 0u;
+          for (int b = 0; b < TB; ++b)
+            if (c < nvc && b < nb && mine(t0 + b, c)) mask |= 1u << b;
+          if (mask != 0u) {  // (warp-uniform)
+            pend[c] = pq_filter_round(t_lane + c * 32, acc, L::acc, NQ, mask, item.b_row0 + t0 * 128 + row, sThr + c * 32, sCnt + c * 32,
+                                      sCand + c * 32 * cap, cap, t_full, aph);
+            any_left |= (pend[c].x | pend[c].y | pend[c].z | pend[c].w) != 0u;
           }
         }
         __syncwarp();
-        mark(0x11 + (t0 << 8));
-        uint32_t rounds = 0;
         while (bar_red_or(1, kEpiThreads, any_left)) {
-          if (P.dbg != nullptr && ++rounds > 4096u) {  // an overflow loop that does not converge: report + trap
-            if (lane == 0 && atomicCAS(P.dbg + blockIdx.x * 16, 0u, 0x4ffu) == 0u) { P.dbg[blockIdx.x * 16 + 2] = static_cast<uint32_t>(it); P.dbg[blockIdx.x * 16 + 3] = t0; }
-            __threadfence_system();
-            __trap();
-          }
           for (int col = ew; col < NQ; col += kEpiWarps)
             if (sCnt[col] > cap) compact(col);  // (warp-uniform: every lane reads the same counter)
           ptx::named_bar_sync(1, kEpiThreads);
@@ -560,12 +631,12 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           for (int b = 0; b < TB; ++b) {
             const uint32_t ab = (acc + b) % L::acc;
 #pragma unroll
-            for (int i = 0; i < MYCH; ++i) {
-              const int c = NCH >= 2 ? 2 * i + half : 0;
+            for (int c = 0; c < NCH; ++c) {
               // re-read from TMEM, re-test against the tightened thresholds.  tcgen05.ld / wait::ld are .sync.aligned: the
               // whole warp executes them together (lanes with nothing pending pass only = 0)
-              if (__any_sync(0xffffffffu, pend[b][i] != 0)) pend[b][i] = do_chunk(t_lane + ab * NQ, item.b_row0 + (t0 + b) * 128 + row, c, pend[b][i]);
-              any_left |= pend[b][i] != 0;
+              uint32_t& pb = b == 0 ? pend[c].x : (b == 1 ? pend[c].y : (b == 2 ? pend[c].z : pend[c].w));
+              if (__any_sync(0xffffffffu, pb != 0)) pb = do_chunk(t_lane + ab * NQ, item.b_row0 + (t0 + b) * 128 + row, c, pb);
+              any_left |= pb != 0;
             }
           }
           __syncwarp();
