@@ -854,16 +854,16 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   // residual rounded to bf16: the same class of approximation, at tensor-core speed.  CUVS_B200_PQ_PATH=lut forces the
   // faithful LUT kernel (bit-level emulation of the fp16 / fp_8bit<5> LUT entries).
   const bool reduced = !(sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F);
-  const bool use_stream = env_path() != 1 && idx.cstream.data() != nullptr && k <= 32;  // (C) codes streamed + decoded on the SM
+  const bool use_stream = env_path() != 1 && idx.cstream.data() != nullptr && k <= 64;  // (C) codes streamed + decoded on the SM
   const bool use_tc     = use_stream || (env_path() == 1 ? false : idx.yhat.data() != nullptr);
   const int passes   = reduced ? 1 : 2;
   const int lists = use_stream ? 1 : (use_tc ? tc_lists_per_item() : 1);
   // candidates kept per (query, probe): the tensor-core epilogue keeps `lists` sorted lists of KC (one per column half of
   // the tile); for k > KC the union of the two half lists stands in for the pair's top-k (exact whenever no more than KC of
   // them fall into one half — an approximation only the k > 32 candidate-generation use case can see)
-  const int KC    = k <= 16 ? 16 : (k <= 32 || use_tc ? 32 : 64);
+  const int KC    = k <= 16 ? 16 : (k <= 32 || (use_tc && !use_stream) ? 32 : 64);
   const int KCW   = KC * lists;
-  B2_EXPECTS(KCW >= k, "ivf_pq search: k = %d > 32 needs an index with decoded rows (CUVS_B200_PQ_KEEP_DECODED=1) or the LUT path (CUVS_B200_PQ_PATH=lut)", k);
+  B2_EXPECTS(KCW >= k, "ivf_pq search: k = %d > 64 needs an index with decoded rows (CUVS_B200_PQ_KEEP_DECODED=1) or the LUT path (CUVS_B200_PQ_PATH=lut)", k);
   // queries per work item: 128 for the query-major kernels; the streamed kernel takes the list rows as the MMA's M side
   // and 32 / 64 / 128 probing queries as N (picked from the average number of pairs per list)
   const int group = use_stream ? pq_stream_group(static_cast<double>(nq) * n_probes / std::max<uint32_t>(idx.n_lists, 1), KC, passes) : 128;

@@ -70,7 +70,7 @@ struct pq_args {
   int kth;
   int n_items_host;
   int KC;
-  int cap;      // candidate buffer entries per query (KC < cap <= 64)
+  int cap;      // candidate buffer entries per query (KC < cap <= 128)
   int cstages;  // code ring depth
   int blk;      // bytes of one tile block of the stream
   int tb_limit;   // tiles per epilogue round (<= layout::tb; CUVS_B200_PQ_TB for bisection)
@@ -250,23 +250,31 @@ __device__ __noinline__ uint4 pq_filter_round(uint32_t taddr, uint32_t buf0, uin
   return make_uint4(l0, l1, l2, l3);
 }
 
-// Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l and l + 32 (64-bit keys
-// order(t) << 32 | ~pos, unique, 0 = none); every entry is broadcast from shared memory and each lane counts how many beat its
-// own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + two compare-adds.
-__device__ __noinline__ void pq_rank_select(const unsigned long long* buf, int n, int lane, unsigned long long& k0, unsigned long long& k1,
-                                            int& r0, int& r1)
+// Selection inside one column's buffer by one warp, rank by counting: lane l holds entries l, l + 32, l + 64, l + 96 (64-bit keys
+// order(t) << 32 | ~pos, unique, 0 = none; n <= 128); every entry is broadcast from shared memory and each lane counts how
+// many beat its own.  rank 0 = best.  No dependent chain: n iterations of one LDS.64 + four compare-adds.
+__device__ __forceinline__ void pq_rank_select(const unsigned long long* buf, int n, int lane, unsigned long long (&k)[4], int (&r)[4])
 {
-  k0 = lane < n ? buf[lane] : 0ull;
-  k1 = lane + 32 < n ? buf[lane + 32] : 0ull;
-  int a = 0, b = 0;
-#pragma unroll 4
-  for (int i = 0; i < n; ++i) {
-    const unsigned long long ki = buf[i];
-    a += ki > k0 ? 1 : 0;
-    b += ki > k1 ? 1 : 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    k[e] = lane + 32 * e < n ? buf[lane + 32 * e] : 0ull;
+    r[e] = 0;
   }
-  r0 = a;
-  r1 = b;
+  if (n <= 64) {  // (warp-uniform) the common case: buffers of <= 64 entries
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const unsigned long long ki = buf[i];
+      r[0] += ki > k[0] ? 1 : 0;
+      r[1] += ki > k[1] ? 1 : 0;
+    }
+  } else {
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+      const unsigned long long ki = buf[i];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[e] += ki > k[e] ? 1 : 0;
+    }
+  }
 }
 
 template <int NQ, int NKB, int PASSES>
@@ -536,23 +544,22 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     constexpr int NCH = NQ / 32;
     uint32_t acc = 0, aph = 0, ss = 0, sp = 0;
 
-    auto rank_select = [&](int col, unsigned long long& k0, unsigned long long& k1, int& r0, int& r1) -> int {
+    auto rank_select = [&](int col, unsigned long long (&k)[4], int (&r)[4]) -> int {
       const int n = min(sCnt[col], cap);
-      pq_rank_select(sCand + col * cap, n, lane, k0, k1, r0, r1);
+      pq_rank_select(sCand + col * cap, n, lane, k, r);
       return n;
     };
     // compaction: keep the KC best at the front, tighten the column's threshold to its kth best
     auto compact = [&](int col) {
-      unsigned long long k0, k1;
-      int r0, r1;
-      const int n = rank_select(col, k0, k1, r0, r1);
+      unsigned long long k[4];
+      int r[4];
+      const int n = rank_select(col, k, r);
       __syncwarp();
       unsigned long long* buf = sCand + col * cap;
-      if (k0 != 0ull && r0 < KC) buf[r0] = k0;
-      if (k1 != 0ull && r1 < KC) buf[r1] = k1;
-      if (n >= kth) {
-        if (k0 != 0ull && r0 == kth - 1) sThr[col] = fmaxf(sThr[col], __uint_as_float(okey_inv(static_cast<uint32_t>(k0 >> 32))));
-        if (k1 != 0ull && r1 == kth - 1) sThr[col] = fmaxf(sThr[col], __uint_as_float(okey_inv(static_cast<uint32_t>(k1 >> 32))));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (k[e] != 0ull && r[e] < KC) buf[r[e]] = k[e];
+        if (n >= kth && k[e] != 0ull && r[e] == kth - 1) sThr[col] = fmaxf(sThr[col], __uint_as_float(okey_inv(static_cast<uint32_t>(k[e] >> 32))));
       }
       if (lane == 0) sCnt[col] = min(n, KC);
       __syncwarp();
@@ -653,9 +660,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
 
       // item done: every column's KC best -> global; publish the query's k-th best for the other items of the same query
       for (int col = ew; col < static_cast<int>(min(item.valid_rows, static_cast<uint32_t>(NQ))); col += kEpiWarps) {
-        unsigned long long k0, k1;
-        int r0, r1;
-        const int n  = rank_select(col, k0, k1, r0, r1);
+        unsigned long long k[4];
+        int r[4];
+        const int n  = rank_select(col, k, r);
         const int nk = min(n, KC);
         const uint32_t arow = item.a_row0 + col;
         const int64_t o     = static_cast<int64_t>(item.out_off) + static_cast<int64_t>(col) * P.out_row_stride;
@@ -669,9 +676,10 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
             atomicMin(P.b_keys + (P.b_idx ? P.b_idx[arow] : arow), kp >= 0 ? kp : kp ^ 0x7fffffff);
           }
         };
-        emit(k0, r0);
-        emit(k1, r1);
-        if (P.out_score != nullptr && lane >= nk && lane < KC) { P.out_score[o + lane] = INFINITY; P.out_pos[o + lane] = 0xffffffffu; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) emit(k[e], r[e]);
+        if (P.out_score != nullptr)
+          for (int slot = nk + lane; slot < KC; slot += 32) { P.out_score[o + slot] = INFINITY; P.out_pos[o + slot] = 0xffffffffu; }
       }
       ptx::named_bar_sync(1, kEpiThreads);  // the next item's column init must not overtake another warp's read-out
     }
@@ -792,8 +800,8 @@ void launch(cudaStream_t stream, int sms, const CUtensorMap& mq_hi, const CUtens
 {
   using L   = layout<NQ, NKB, PASSES>;
   auto kern = pq_stream_scan_kernel<NQ, NKB, PASSES>;
-  a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 64) : 64;  // free slots between compactions: cap - KC
-  if (const int cap_env = env_int("CUVS_B200_PQ_CAP", 0)) a.cap = std::max(a.KC + 8, std::min(64, cap_env));  // bisection knob
+  a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 64) : (a.KC <= 32 ? 64 : 128);  // free slots between compactions: cap - KC
+  if (const int cap_env = env_int("CUVS_B200_PQ_CAP", 0)) a.cap = std::max(a.KC + 8, std::min(a.KC <= 32 ? 64 : 128, cap_env));  // bisection knob
   const int fixed = L::off_cand + NQ * a.cap * 8 + 1024 /*alignment slack of the dynamic segment*/;
   a.cstages = std::min(kMaxCStages, (kSmemLimit - fixed) / a.blk);
   a.tb_limit = std::max(1, std::min(L::tb, env_int("CUVS_B200_PQ_TB", L::tb)));
@@ -879,6 +887,7 @@ int pq_stream_group(double pairs_per_list, int KC, int passes)
   int g = pairs_per_list <= 20.0 ? 32 : (pairs_per_list <= 80.0 ? 64 : 128);
   if (forced == 32 || forced == 64 || forced == 128) g = forced;
   if ((KC > 16 || passes == 2) && g > 64) g = 64;  // shared-memory budget: wide candidate buffers / two residual planes
+  if (KC > 32) g = 32;                             // 128-entry buffers (k in 33..64): 32 query columns per item
   return g;
 }
 
@@ -889,9 +898,9 @@ void pq_stream_scan(cudaStream_t stream, int device, const __nv_bfloat16* q_hi, 
 {
   if (n_items == 0) return;
   B2_EXPECTS(Kp == 2 * pq_dim && (pq_dim == 32 || pq_dim == 64), "pq_stream_scan: pq_dim must be 32 or 64 with pq_len 2 (Kp=%d)", Kp);
-  B2_EXPECTS(KC == 16 || KC == 32, "pq_stream_scan: KC must be 16 or 32");
+  B2_EXPECTS(KC == 16 || KC == 32 || KC == 64, "pq_stream_scan: KC must be 16, 32 or 64");
   B2_EXPECTS(passes == 1 || (passes == 2 && q_lo != nullptr), "pq_stream_scan: passes must be 1, or 2 with a lo plane");
-  B2_EXPECTS(group == 32 || group == 64 || (group == 128 && KC == 16 && passes == 1), "pq_stream_scan: unsupported group %d", group);
+  B2_EXPECTS(group == 32 || (group == 64 && KC <= 32) || (group == 128 && KC == 16 && passes == 1), "pq_stream_scan: unsupported group %d", group);
   B2_EXPECTS(a_rows >= group, "pq_stream_scan: the residual plane must hold at least one group of rows");
   pq_args a{};
   a.stream = code_stream;

@@ -268,6 +268,25 @@ def test_streamed_scan_all_shapes(small_index, stream_index_128, group, which, k
     assert all(len(set(r.tolist())) == k for r in i) and (i >= 0).all() and (i < len(ds)).all()
 
 
+@pytest.mark.parametrize("k", [40, 64])
+def test_streamed_scan_k_up_to_64(stream_index_128, k):
+    """k in 33..64 (refine_ratio x k candidate generation): 64 kept entries per (query, probe), 128-entry buffers, 32-query work
+    items — same answers as the reference-formulation LUT kernel and the oracle."""
+    ds, qs, index = stream_index_128
+    assert index.streamed
+    d, i = _search(index, qs, 8, k, "tc", lut_dtype=np.float16)
+    rd, ri = _oracle(index, qs, 8, k, "sqeuclidean", "f16", "f32")
+    assert oracle.recall_with_ties(i, d, ri, rd, eps=1e-2) >= 0.975
+    assert all(len(set(r.tolist())) == k for r in i) and (i >= 0).all() and (i < len(ds)).all()
+    d2, i2 = _search(index, qs, 8, k, "lut", lut_dtype=np.float16)
+    same = np.mean([len(set(a) & set(b)) / float(k) for a, b in zip(i, i2)])
+    assert same >= 0.97, same
+    # the 2-pass scan (fp32 LUT semantics) through the same wide buffers
+    d3, i3 = _search(index, qs, 8, k, "tc")
+    rd3, ri3 = _oracle(index, qs, 8, k, "sqeuclidean", "f32", "f32")
+    assert oracle.recall_with_ties(i3, d3, ri3, rd3, eps=2e-3) >= 0.99
+
+
 def test_streamed_index_keeps_no_decoded_rows(stream_index_128):
     ds, qs, index = stream_index_128
     assert index.streamed
