@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcuvs_c.so")
+LIB_PATH = os.environ.get("CUVS_B200_LIB") or os.path.join(_HERE, "lib", "libcuvs_c.so")  # (override: A/B builds of the same sources)
 
 
 class CuvsError(RuntimeError):

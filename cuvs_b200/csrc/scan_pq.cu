@@ -42,7 +42,12 @@ namespace b200 {
 namespace {
 
 constexpr int kDecWarps   = 8;
-constexpr int kEpiWarps   = 8;   // two per TMEM lane quarter: each owns every other 32-column chunk of the accumulator
+#ifndef CUVS_B200_PQ_EPI_WARPS
+#define CUVS_B200_PQ_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps   = CUVS_B200_PQ_EPI_WARPS;  // kEpiPerQ per TMEM lane quarter: they split the (tile, chunk) units of a round
+constexpr int kEpiPerQ    = kEpiWarps / 4;
+static_assert(kEpiWarps % 4 == 0 && kEpiPerQ >= 2 && kEpiPerQ <= 4, "epilogue warps come in groups of four (one per lane quarter)");
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads    = 64 + 32 * kDecWarps + kEpiThreads;  // 576
 constexpr int kEpiWarp0   = 2 + kDecWarps;                      // first epilogue warp (10: warp & 3 covers all TMEM quarters)
@@ -191,7 +196,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
 // taddr = TMEM address of the chunk in accumulator buffer 0; tile b of the round sits in buffer (buf0 + b) % nacc (nq columns
 // per buffer) and is waited for here (t_full, parity aph, flipped where the buffer index wraps); mask = tiles of the round this
 // warp owns (warp-uniform: tcgen05.ld is .sync.aligned).  Returns, per tile, the columns whose candidate could not be stored.
-__device__ __noinline__ uint4 pq_filter_round(uint32_t taddr, uint32_t buf0, uint32_t nacc, uint32_t nq, uint32_t mask, uint32_t pos0,
+__device__ __forceinline__ uint4 pq_filter_round(uint32_t taddr, uint32_t buf0, uint32_t nacc, uint32_t nq, uint32_t mask, uint32_t pos0,
                                               const float* __restrict__ thr, int* cnt, unsigned long long* cand, int cap,
                                               uint64_t* t_full, uint32_t aph)
 {
@@ -535,7 +540,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
     // ------------------------------------------------------------------ epilogue: thread = list row, columns = queries
     const int ew      = warp - kEpiWarp0;
     const int quarter = warp & 3;
-    const int half    = ew >> 2;  // which of the lane quarter's two warps: they split the round's (tile, chunk) units
+    const int half    = ew >> 2;  // which of the lane quarter's kEpiPerQ warps: they split the round's (tile, chunk) units
     const int row     = quarter * 32 + lane;
     const int te      = static_cast<int>(threadIdx.x) - 32 * kEpiWarp0;  // 0..127
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -609,19 +614,26 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
       // <= 32 probing queries (most items of a sparsely probed index) keeps BOTH warps busy on alternating tiles instead of
       // sending one of them through 32 columns of +inf thresholds.
       const int nvc = min(NCH, (static_cast<int>(item.valid_rows) + 31) >> 5);
-      auto mine = [&](uint32_t t, int c) -> bool { return (((nvc & 1) ? (t + c) : static_cast<uint32_t>(c)) & 1u) == static_cast<uint32_t>(half); };
       // rounds of TB tiles: all their accumulators are filtered, then ONE barrier decides whether any buffer overflowed
       for (uint32_t t0 = 0; t0 < item.n_tiles; t0 += min(TB, P.tb_limit)) {
         const int nb = static_cast<int>(min(static_cast<uint32_t>(min(TB, P.tb_limit)), item.n_tiles - t0));
         uint4 pend[NCH];  // per chunk: .x/.y/.z/.w = columns still pending in tile 0..3 of the round
         bool any_left = false;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          pend[c] = make_uint4(0u, 0u, 0u, 0u);
-          uint32_t mask = 0;
+        for (int c = 0; c < NCH; ++c) pend[c] = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t live = (1u << nb) - 1u;
+#pragma unroll 1  // ONE inlined copy of the round filter (its call overhead was ~15 % of the epilogue's instructions)
+        for (int c = 0; c < nvc; ++c) {
+          // tiles of the round whose (tile, c) unit is this warp's: all or none for an even chunk count, every other one else
+          uint32_t mask;
+          if (kEpiPerQ == 2) {
+            mask = live & ((nvc & 1) ? (0x55555555u << ((t0 + c + half) & 1u)) : ((c & 1) == half ? 0xffffffffu : 0u));
+          } else {  // unit (t, c) -> warp ((t * nvc + c) mod kEpiPerQ) of the quarter
+            mask = 0u;
 #pragma unroll
-          for (int b = 0; b < TB; ++b)
-            if (c < nvc && b < nb && mine(t0 + b, c)) mask |= 1u << b;
+            for (int b = 0; b < TB; ++b)
+              if (b < nb && static_cast<int>(((t0 + b) * nvc + c) % kEpiPerQ) == half) mask |= 1u << b;
+          }
           if (mask != 0u) {  // (warp-uniform)
             pend[c] = pq_filter_round(t_lane + c * 32, acc, L::acc, NQ, mask, item.b_row0 + t0 * 128 + row, sThr + c * 32, sCnt + c * 32,
                                       sCand + c * 32 * cap, cap, t_full, aph);

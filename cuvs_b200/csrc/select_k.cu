@@ -208,14 +208,15 @@ constexpr int kRegEqCap   = 1024;
 constexpr int kRegMaxK    = 256;
 
 template <int E, typename IdxIn, typename IdxOut, bool HasIdx>
-__global__ void __launch_bounds__(kRegThreads) select_k_reg_kernel(const float* __restrict__ in_val, const IdxIn* __restrict__ in_idx,
+__global__ void __launch_bounds__(kRegThreads, E <= 32 ? 2 : 1) select_k_reg_kernel(const float* __restrict__ in_val, const IdxIn* __restrict__ in_idx,
                                                                    int64_t len, int64_t in_ld, int k, float* __restrict__ out_val,
                                                                    IdxOut* __restrict__ out_idx, bool select_min)
 {
-  __shared__ uint32_t hist[kRegBins];
+  __shared__ __align__(16) uint32_t hist[kRegBins];
   __shared__ unsigned long long okeys[kRegMaxK];
   __shared__ unsigned long long ebuf[kRegEqCap];
-  __shared__ unsigned long long red[2 * (kRegThreads / 32)];
+  __shared__ uint32_t red[2 * (kRegThreads / 32)];
+  __shared__ uint32_t wtot[kRegThreads / 32];
   __shared__ uint32_t scal[8];  // [0] threshold bucket [1] keys below it [2] keys in it [3] winners stored [4] bucket keys stored
 
   const int64_t row = blockIdx.x;
@@ -224,33 +225,26 @@ __global__ void __launch_bounds__(kRegThreads) select_k_reg_kernel(const float* 
   const int k_eff = len < k ? static_cast<int>(len) : k;
 
   uint32_t u[E];
-  unsigned long long mn = ~0ull, mx = 0ull;
+  uint32_t mn = 0xffffffffu, mx = 0u;  // bounds on the 32-bit keys are enough: the span only has to COVER the composites
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const int64_t i = static_cast<int64_t>(j) * kRegThreads + tid;
     u[j] = 0u;
     if (i < len) {
       u[j] = f2key(v[i], select_min);
-      const unsigned long long K = (static_cast<unsigned long long>(u[j]) << 32) | static_cast<uint32_t>(i);
-      mn = K < mn ? K : mn;
-      mx = K > mx ? K : mx;
+      mn   = min(mn, u[j]);
+      mx   = max(mx, u[j]);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-    mn = a < mn ? a : mn;
-    mx = b > mx ? b : mx;
-  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) { red[wid] = mn; red[kRegThreads / 32 + wid] = mx; }
   if (tid == 0) { scal[3] = 0; scal[4] = 0; }
   __syncthreads();
-  unsigned long long lo = red[0], hi = red[kRegThreads / 32];
-#pragma unroll
-  for (int w = 1; w < kRegThreads / 32; ++w) {
-    lo = red[w] < lo ? red[w] : lo;
-    hi = red[kRegThreads / 32 + w] > hi ? red[kRegThreads / 32 + w] : hi;
-  }
+  uint32_t lo32 = red[lane & (kRegThreads / 32 - 1)], hi32 = red[kRegThreads / 32 + (lane & (kRegThreads / 32 - 1))];
+  lo32 = __reduce_min_sync(0xffffffffu, lo32);
+  hi32 = __reduce_max_sync(0xffffffffu, hi32);
+  unsigned long long lo = static_cast<unsigned long long>(lo32) << 32, hi = (static_cast<unsigned long long>(hi32) << 32) | 0xffffffffull;
   unsigned long long span = hi - lo;  // keys in play: lo <= K <= lo + span
   uint32_t need = static_cast<uint32_t>(k_eff);
 
@@ -265,21 +259,28 @@ __global__ void __launch_bounds__(kRegThreads) select_k_reg_kernel(const float* 
       if (i < len && K >= lo && K - lo <= span) atomicAdd(&hist[static_cast<uint32_t>((K - lo) >> s)], 1u);
     }
     __syncthreads();
-    if (wid == 0) {
-      uint32_t sum = 0;
-      for (int b = 0; b < kRegBins / 32; ++b) sum += hist[lane * (kRegBins / 32) + b];
+    {
+      // two-level scan, all 16 warps: warp w owns buckets [128 w, 128 w + 128), lane l four of them (one conflict-free 128-bit load)
+      static_assert(kRegBins == 4 * kRegThreads, "one uint4 of buckets per thread");
+      const uint4 h4 = reinterpret_cast<const uint4*>(hist)[tid];
+      const uint32_t sum = h4.x + h4.y + h4.z + h4.w;
       uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
+      if (lane == 31) wtot[wid] = incl;
+      __syncthreads();
       uint32_t c = incl - sum;
-      if (c < need && need <= incl) {
-        for (int b = 0; b < kRegBins / 32; ++b) {
-          const uint32_t h = hist[lane * (kRegBins / 32) + b];
-          if (c < need && need <= c + h) { scal[0] = lane * (kRegBins / 32) + b; scal[1] = c; scal[2] = h; }
-          c += h;
+#pragma unroll
+      for (int w = 0; w < kRegThreads / 32; ++w) c += w < wid ? wtot[w] : 0u;
+      if (c < need && need <= c + sum) {  // exactly one thread: the bucket where the running count reaches `need`
+        const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (c < need && need <= c + h[e]) { scal[0] = tid * 4 + e; scal[1] = c; scal[2] = h[e]; }
+          c += h[e];
         }
       }
     }
@@ -339,6 +340,14 @@ void launch(cudaStream_t stream, const float* in_val, const void* in_idx, int64_
   if (len >= 2048 && len <= 64 * kRegThreads && k <= kRegMaxK && getenv("CUVS_B200_SELECT_RADIX") == nullptr) {
     count_launch();
     const unsigned grid = static_cast<unsigned>(batch);
+    static bool carve = [] {  // two resident CTAs need ~40 KB of shared memory: ask for the carve-out once per instantiation
+      cudaFuncSetAttribute(select_k_reg_kernel<8, IdxIn, IdxOut, HasIdx>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+      cudaFuncSetAttribute(select_k_reg_kernel<16, IdxIn, IdxOut, HasIdx>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+      cudaFuncSetAttribute(select_k_reg_kernel<32, IdxIn, IdxOut, HasIdx>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+      cudaFuncSetAttribute(select_k_reg_kernel<64, IdxIn, IdxOut, HasIdx>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+      return true;
+    }();
+    (void)carve;
     auto ii = static_cast<const IdxIn*>(in_idx);
     auto oo = static_cast<IdxOut*>(out_idx);
     if (len <= 8 * kRegThreads) select_k_reg_kernel<8, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
