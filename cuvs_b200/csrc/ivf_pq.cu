@@ -576,12 +576,32 @@ void refresh_decoded(resources* res, ivf_pq_index& idx)
   static const bool keep_decoded = getenv("CUVS_B200_PQ_KEEP_DECODED") != nullptr;  // A/B experiments against path (B)
   if (!keep_decoded && idx.Kp == idx.rot_dim &&
       pq_stream_supported(res->device, idx.pq_dim, idx.pq_len, idx.pq_bits, idx.codebook_kind == CUVS_IVF_PQ_CODEBOOK_GEN_PER_SUBSPACE)) {
-    idx.yhat.release();
-    idx.hx.release();
     idx.cstream.alloc(static_cast<size_t>(std::max<int64_t>(R / 128, 1)) * pq_stream_tile_bytes(idx.pq_dim));
     idx.cb_words.alloc(static_cast<size_t>(idx.pq_dim / 32) * 256 * 32);
     pq_stream_build(s, idx.codes.data(), idx.ids.data(), kPadId, R, idx.pq_dim, idx.pq_centers.data(), is_ip(idx.metric),
                     idx.cstream.data(), idx.cb_words.data());
+    // A SMALL index additionally caches its decoded rows (2 * rot_dim bytes per vector, derived data): when a batch sends
+    // hundreds of queries to every list (10M vectors / 1024 lists / 10k x 64 probes = 625 per list) the stream kernel would
+    // decode each list once per 64 probing queries, and reading rows decoded once at build time is the better trade.  The
+    // search picks per call (dense_probing below).  Budget: CUVS_B200_PQ_DECODED_BUDGET_MB (default 4096, 0 = never).
+    const char* bm        = getenv("CUVS_B200_PQ_DECODED_BUDGET_MB");
+    const int64_t budget  = (bm ? atoll(bm) : 4096) << 20;
+    const bool also_rows  = R > 0 && static_cast<int64_t>(R) * idx.Kp * 2 <= budget;
+    if (also_rows) {
+      idx.yhat.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * idx.Kp);
+      idx.hx.alloc(static_cast<size_t>(std::max<int64_t>(R, 128)) * 16);
+      dbuf<float> hn(static_cast<size_t>(R), s);
+      count_launch();
+      pq_decode_kernel<<<blocks_for(R * 32, 256), 256, 0, s>>>(idx.codes.data(), idx.ids.data(), R, idx.pq_dim, idx.pq_len, idx.book(),
+                                                               idx.Kp, idx.pq_centers.data(), false, idx.lists.d_offsets.data(), idx.n_lists,
+                                                               is_ip(idx.metric), idx.centers_rot.data(), idx.rot_dim, idx.yhat.data(),
+                                                               hn.data());
+      B2_CUDA(cudaGetLastError());
+      tc_pack_half_norms(s, hn.data(), R, idx.hx.data());
+    } else {
+      idx.yhat.release();
+      idx.hx.release();
+    }
     static const bool keep_flat = getenv("CUVS_B200_PQ_KEEP_FLAT") != nullptr;
     if (!keep_flat && R > 0) {  // the stream is the index: pq_dim + 4 bytes per vector (+ 8 for the id)
       B2_CUDA(cudaStreamSynchronize(s));
@@ -800,7 +820,7 @@ int env_path()  // read on every search: tests switch paths inside one process
 {
   const char* e = getenv("CUVS_B200_PQ_PATH");
   if (!e) return 0;
-  return strcmp(e, "lut") == 0 ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0);
+  return strcmp(e, "lut") == 0 ? 1 : (strcmp(e, "tc") == 0 ? 2 : (strcmp(e, "stream") == 0 ? 3 : 0));  // stream: never the decoded-row cache
 }
 
 void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearchParams& sp, const DLTensor& qt, const DLTensor& nt,
@@ -854,7 +874,11 @@ void ivf_pq_search(resources* res, const ivf_pq_index& idx, const cuvsIvfPqSearc
   // residual rounded to bf16: the same class of approximation, at tensor-core speed.  CUVS_B200_PQ_PATH=lut forces the
   // faithful LUT kernel (bit-level emulation of the fp16 / fp_8bit<5> LUT entries).
   const bool reduced = !(sp.lut_dtype == CUDA_R_32F && sp.internal_distance_dtype == CUDA_R_32F);
-  const bool use_stream = env_path() != 1 && idx.cstream.data() != nullptr && k <= 64;  // (C) codes streamed + decoded on the SM
+  // (C) codes streamed + decoded on the SM — unless the index is small enough to also hold decoded rows AND this batch probes
+  // densely (>= 128 queries per list on average: the per-group decode would be repeated more than twice per list)
+  const bool dense_probing = idx.yhat.data() != nullptr && k <= 32 && env_path() != 3 &&
+                             static_cast<double>(nq) * n_probes >= 128.0 * std::max<uint32_t>(idx.n_lists, 1);
+  const bool use_stream = env_path() != 1 && idx.cstream.data() != nullptr && k <= 64 && !dense_probing;
   const bool use_tc     = use_stream || (env_path() == 1 ? false : idx.yhat.data() != nullptr);
   const int passes   = reduced ? 1 : 2;
   const int lists = use_stream ? 1 : (use_tc ? tc_lists_per_item() : 1);
@@ -1028,7 +1052,7 @@ cuvsError_t cuvsB200IvfPqIndexInfo(cuvsIvfPqIndex_t index, int* path, int64_t* d
 {
   return guarded([=] {
     const ivf_pq_index& idx = pq_of(index);
-    if (path) *path = idx.cstream.data() ? 2 : (idx.yhat.data() ? 1 : 0);
+    if (path) *path = (idx.cstream.data() ? 2 : 0) | (idx.yhat.data() ? 1 : 0);
     if (device_bytes)
       *device_bytes = static_cast<int64_t>(idx.codes.size() + idx.ids.size() * 8 + idx.cstream.size() + idx.cb_words.size() * 4 +
                                            idx.yhat.size() * 2 + idx.hx.size() * 2 + idx.centers.size() * 4 + idx.centers_ext.size() * 4 +

@@ -813,7 +813,7 @@ void launch(cudaStream_t stream, int sms, const CUtensorMap& mq_hi, const CUtens
   using L   = layout<NQ, NKB, PASSES>;
   auto kern = pq_stream_scan_kernel<NQ, NKB, PASSES>;
   a.cap     = a.KC <= 16 ? (NQ == 128 ? 32 : 64) : (a.KC <= 32 ? 64 : 128);  // free slots between compactions: cap - KC
-  if (const int cap_env = env_int("CUVS_B200_PQ_CAP", 0)) a.cap = std::max(a.KC + 8, std::min(a.KC <= 32 ? 64 : 128, cap_env));  // bisection knob
+  if (const int cap_env = env_int("CUVS_B200_PQ_CAP", 0)) a.cap = std::max(a.KC + 8, std::min(128, cap_env));  // bisection knob
   const int fixed = L::off_cand + NQ * a.cap * 8 + 1024 /*alignment slack of the dynamic segment*/;
   a.cstages = std::min(kMaxCStages, (kSmemLimit - fixed) / a.blk);
   a.tb_limit = std::max(1, std::min(L::tb, env_int("CUVS_B200_PQ_TB", L::tb)));

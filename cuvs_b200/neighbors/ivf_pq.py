@@ -117,7 +117,8 @@ class Index:
         check(lib.cuvsB200IvfPqIndexInfo(self._p, C.byref(path), C.byref(nbytes)))
         return path.value, nbytes.value
 
-    streamed = property(lambda self: self._info()[0] == 2)       # served by the code-streaming scan (scan_pq.cu)
+    streamed = property(lambda self: (self._info()[0] & 2) != 0)  # holds the code stream (code-streaming scan, scan_pq.cu)
+    has_decoded_rows = property(lambda self: (self._info()[0] & 1) != 0)  # decoded bf16 rows (small-index cache / decoded-row scan)
     device_bytes = property(lambda self: self._info()[1])        # bytes of device memory the index holds
 
     def _view(self, fn, *args):

@@ -45,7 +45,9 @@ CUVS_EXPORT cuvsError_t cuvsB200IvfFlatGetSize(cuvsIvfFlatIndex_t index, int64_t
 CUVS_EXPORT cuvsError_t cuvsB200IvfFlatSetCenters(cuvsResources_t res, cuvsIvfFlatIndex_t index, DLManagedTensor* centers);
 
 /* IVF-PQ: which fine-scan kernel cuvsIvfPqSearch will use on this index by default, and the device bytes the index holds.
- * *path: 2 = code-streaming tcgen05 scan (scan_pq.cu), 1 = decoded-row tcgen05 scan (scan_tc.cu), 0 = LUT kernel. */
+ * *path: bit 1 (value 2) = the index holds the code stream (code-streaming tcgen05 scan, scan_pq.cu), bit 0 (value 1) = it holds
+ * decoded bf16 rows (decoded-row tcgen05 scan, scan_tc.cu; on a streamed index: the small-index cache used by densely probing
+ * batches), 0 = LUT kernel only. */
 CUVS_EXPORT cuvsError_t cuvsB200IvfPqIndexInfo(cuvsIvfPqIndex_t index, int* path, int64_t* device_bytes);
 
 /* ---- multi-GPU exchange step (one process per GPU) ------------------------------------------------

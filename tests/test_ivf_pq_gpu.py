@@ -258,7 +258,7 @@ def test_streamed_scan_all_shapes(small_index, stream_index_128, group, which, k
     os.environ["CUVS_B200_PQ_GROUP"] = str(group)
     try:
         kw = {} if lut == "f32" else {"lut_dtype": np.float16}
-        d, i = _search(index, qs, 8, k, "tc", **kw)
+        d, i = _search(index, qs, 8, k, "stream", **kw)
     finally:
         del os.environ["CUVS_B200_PQ_GROUP"]
     rd, ri = _oracle(index, qs, 8, k, "sqeuclidean", lut, "f32")
@@ -274,7 +274,7 @@ def test_streamed_scan_k_up_to_64(stream_index_128, k):
     items — same answers as the reference-formulation LUT kernel and the oracle."""
     ds, qs, index = stream_index_128
     assert index.streamed
-    d, i = _search(index, qs, 8, k, "tc", lut_dtype=np.float16)
+    d, i = _search(index, qs, 8, k, "stream", lut_dtype=np.float16)
     rd, ri = _oracle(index, qs, 8, k, "sqeuclidean", "f16", "f32")
     assert oracle.recall_with_ties(i, d, ri, rd, eps=1e-2) >= 0.975
     assert all(len(set(r.tolist())) == k for r in i) and (i >= 0).all() and (i < len(ds)).all()
@@ -282,17 +282,37 @@ def test_streamed_scan_k_up_to_64(stream_index_128, k):
     same = np.mean([len(set(a) & set(b)) / float(k) for a, b in zip(i, i2)])
     assert same >= 0.97, same
     # the 2-pass scan (fp32 LUT semantics) through the same wide buffers
-    d3, i3 = _search(index, qs, 8, k, "tc")
+    d3, i3 = _search(index, qs, 8, k, "stream")
     rd3, ri3 = _oracle(index, qs, 8, k, "sqeuclidean", "f32", "f32")
     assert oracle.recall_with_ties(i3, d3, ri3, rd3, eps=2e-3) >= 0.99
 
 
-def test_streamed_index_keeps_no_decoded_rows(stream_index_128):
-    ds, qs, index = stream_index_128
+def test_streamed_index_keeps_no_decoded_rows():
+    """Beyond the decoded-row budget (here: 0) the code stream is the whole index: codes + half-norms + ids per vector."""
+    m = _mod()
+    ds, centers = clustered(40000, 128, 15, n_centers=64)
+    os.environ["CUVS_B200_PQ_DECODED_BUDGET_MB"] = "0"
+    try:
+        index = m.build(m.IndexParams(n_lists=64, pq_dim=64, kmeans_n_iters=10), torch.from_numpy(ds).cuda())
+    finally:
+        del os.environ["CUVS_B200_PQ_DECODED_BUDGET_MB"]
     assert index.streamed
-    # codes (64 B) + code stream (68 B) + ids (8 B) per vector, padded lists, + quantizers: well under the 288 B/vector
-    # the decoded-row layout alone would take
+    # code stream (68 B) + ids (8 B) per vector, padded lists, + quantizers: well under the 256 B/vector of decoded rows
     assert index.device_bytes < len(ds) * 200
+
+
+def test_small_index_dense_batch_takes_the_decoded_row_cache(stream_index_128):
+    """A small index also caches decoded rows; a batch with >= 128 probing queries per list is served from them, a sparse one
+    from the code stream: both must agree with each other (same arithmetic: bf16 residual x bf16 codebook rows)."""
+    ds, qs, index = stream_index_128
+    assert index.streamed and index.device_bytes > len(ds) * 256   # the cache is there
+    q = np.concatenate([qs] * 4)[:1100]                             # 1100 queries x 8 probes / 64 lists = 137 per list: dense
+    d_dense, i_dense = _search(index, q, 8, 10, "auto", lut_dtype=np.float16)
+    d_str, i_str = _search(index, q, 8, 10, "stream", lut_dtype=np.float16)
+    same = np.mean([len(set(a) & set(b)) / 10.0 for a, b in zip(i_dense, i_str)])
+    assert same >= 0.995, same
+    rd, ri = _oracle(index, q, 8, 10, "sqeuclidean", "f16", "f32")
+    assert oracle.recall_with_ties(i_dense, d_dense, ri, rd, eps=1e-2) >= 0.975
 
 
 def test_streamed_scan_empty_and_tiny_lists():
@@ -302,7 +322,7 @@ def test_streamed_scan_empty_and_tiny_lists():
     qs = uniform(40, 64, 6, -1, 1)
     index = m.build(m.IndexParams(n_lists=128, pq_dim=32, kmeans_n_iters=4, kmeans_trainset_fraction=1.0), torch.from_numpy(ds).cuda())
     assert index.streamed
-    d, i = _search(index, qs, 128, 10, "tc", lut_dtype=np.float16)
+    d, i = _search(index, qs, 128, 10, "stream", lut_dtype=np.float16)
     rd, ri = _oracle(index, qs, 128, 10, "sqeuclidean", "f16", "f32")
     assert oracle.recall_with_ties(i, d, ri, rd, eps=1e-2) >= 0.99
 
@@ -316,7 +336,7 @@ def test_streamed_scan_is_invariant_to_the_work_item_width(stream_index_128):
     for g in (32, 64, 128):
         os.environ["CUVS_B200_PQ_GROUP"] = str(g)
         try:
-            res[g] = _search(index, qs, 8, 10, "tc", lut_dtype=np.float16)
+            res[g] = _search(index, qs, 8, 10, "stream", lut_dtype=np.float16)
         finally:
             del os.environ["CUVS_B200_PQ_GROUP"]
     for g in (64, 128):
