@@ -473,6 +473,8 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
 #pragma unroll
     for (int x = 0; x < 8; ++x) offx[x] = x * 128 + ((((lane >> 2) ^ x) & 7) << 4) + ((lane & 3) << 2);
     const uint8_t* cb_lane = reinterpret_cast<const uint8_t*>(sCb) + lane * 4;
+    const uint32_t cb_lane32 = ptx::smem_u32(sCb) + static_cast<uint32_t>(lane) * 4u;
+    (void)cb_lane32;
     uint32_t cs = 0, cph = 0, ds = 0, dph = 0, ss = 0, sp = 0;
     for (;;) {
       wait_dbg(P.dbg, &s_full[ss], sp, 0x301, ss, 0);
@@ -487,7 +489,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
         uint4 cw[NKB];
 #pragma unroll
         for (int h = 0; h < NKB; ++h) cw[h] = *reinterpret_cast<const uint4*>(cst + dw * (NKB * 512) + h * 512 + lane * 16);
-        const float hn = reinterpret_cast<const float*>(cst + NKB * 4096)[16 * dw + (lane & 15)];
+        const float hn = reinterpret_cast<const float*>(cst + NKB * 4096)[16 * dw + (lane >> 1)];
         // The ring slot is handed back only AFTER the decode below has consumed these registers.  An mbarrier arrive issued
         // right behind the loads does not wait for them: the arrive is not ordered behind outstanding LDS (the hardware only
         // scoreboards register USE), and under the tensor core's operand traffic a load can sit in the queue longer than the
@@ -505,8 +507,15 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           uint32_t val[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
+#ifdef CUVS_B200_PQ_LEA
+            // byte extract (PRMT) + scaled add (LEA) on a 32-bit shared address: 2 integer instructions per entry instead of
+            // the shift / mask-or / add-base triple the generic-pointer form compiles to
+            const uint32_t c = __byte_perm(w4[i >> 2], 0u, 0x4440u | static_cast<uint32_t>(i & 3));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(val[i]) : "r"(cb_lane32 + static_cast<uint32_t>(h) * 32768u + (c << 7)));
+#else
             const uint32_t c = (w4[i >> 2] >> ((i & 3) * 8)) & 0xffu;
             val[i] = *reinterpret_cast<const uint32_t*>(cb_lane + h * 32768 + c * 128);
+#endif
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -514,7 +523,9 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
         }
         {
           // -hn/2 as three bf16 pieces (exact), identical in both 16-byte chunks of the row; +inf (padding) -> -inf.
-          // Lane l writes chunk l / 16 of row l % 16: 32 distinct 16-byte slots of one 512-byte span (conflict-free)
+          // Lane l writes chunk l % 2 of row l / 2: the warp's 32 x 16 bytes are one contiguous 512-byte span, so every
+          // quarter-warp of the 128-bit store covers 128 consecutive bytes = all 32 banks once (row-major lanes, l % 16 = row,
+          // put lanes 0..7 at a 32-byte stride: a 2-way conflict on every store, 4 excess wavefronts per warp and tile in ncu)
           const float hh = -0.5f * hn;
           __nv_bfloat16 p0 = __float2bfloat16_rn(hh), p1 = __float2bfloat16_rn(0.f), p2 = p1;
           if (!isinf(hh)) {
@@ -524,7 +535,7 @@ pq_stream_scan_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_c
           }
           const uint32_t w0 = static_cast<uint32_t>(__bfloat16_as_ushort(p0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(p1)) << 16);
           const uint32_t w1 = static_cast<uint32_t>(__bfloat16_as_ushort(p2));
-          *reinterpret_cast<uint4*>(sDec + ds * L::dec_stage + NKB * kDecTile + (16 * dw + (lane & 15)) * 32 + (lane >> 4) * 16) =
+          *reinterpret_cast<uint4*>(sDec + ds * L::dec_stage + NKB * kDecTile + (16 * dw) * 32 + lane * 16) =
             make_uint4(w0, w1, 0u, 0u);
         }
         // every loaded register (codes of both halves, half-norm) has fed an issued instruction by now: release the slot

@@ -13,6 +13,7 @@
 
 #include <cuvs/selection/select_k.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -210,7 +211,7 @@ constexpr int kRegMaxK    = 256;
 template <int E, typename IdxIn, typename IdxOut, bool HasIdx>
 __global__ void __launch_bounds__(kRegThreads, E <= 32 ? 2 : 1) select_k_reg_kernel(const float* __restrict__ in_val, const IdxIn* __restrict__ in_idx,
                                                                    int64_t len, int64_t in_ld, int k, float* __restrict__ out_val,
-                                                                   IdxOut* __restrict__ out_idx, bool select_min)
+                                                                   IdxOut* __restrict__ out_idx, bool select_min, int sample_elems)
 {
   __shared__ __align__(16) uint32_t hist[kRegBins];
   __shared__ unsigned long long okeys[kRegMaxK];
@@ -245,12 +246,37 @@ __global__ void __launch_bounds__(kRegThreads, E <= 32 ? 2 : 1) select_k_reg_ker
   lo32 = __reduce_min_sync(0xffffffffu, lo32);
   hi32 = __reduce_max_sync(0xffffffffu, hi32);
   unsigned long long lo = static_cast<unsigned long long>(lo32) << 32, hi = (static_cast<unsigned long long>(hi32) << 32) | 0xffffffffull;
-  unsigned long long span = hi - lo;  // keys in play: lo <= K <= lo + span
+  const unsigned long long full_span = hi - lo;
+  unsigned long long span = full_span;  // keys in play: lo <= K <= lo + span
   uint32_t need = static_cast<uint32_t>(k_eff);
+
+  // Sampled upper bound.  k << len (48 probes out of 16k centres): binning the whole row spends one shared-memory atomic per
+  // element on keys that cannot win.  Take the first `es` elements of every thread as a sample (es * 32 per warp, strided over
+  // the row), T = max over the warps of the warp's sample MINIMUM: every warp has a key <= T, and for es * 32 ~ 0.7 len / k
+  // about 1 % .. 3 % of the row lies below T, of which the k-th smallest is one with overwhelming probability (k = 48,
+  // len = 16384: miss rate ~ 4e-5 on exchangeable data).  The first binning round then only counts keys <= T; if fewer than
+  // `need` keys are there (adversarial order, e.g. a sorted row) the round is repeated over the full span — exactness never
+  // depends on the sample.  CUVS_B200_SELECT_NOSAMPLE=1 (read by the launcher: sample_elems = 0) turns it off.
+  if (sample_elems > 0) {
+    uint32_t smin = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int64_t i = static_cast<int64_t>(j) * kRegThreads + tid;
+      if (j < sample_elems && i < len) smin = min(smin, u[j]);
+    }
+    smin = __reduce_min_sync(0xffffffffu, smin);
+    __syncthreads();  // (red[] is still being read above)
+    if (lane == 0) red[wid] = smin;
+    __syncthreads();
+    uint32_t t32 = red[lane & (kRegThreads / 32 - 1)];
+    t32 = __reduce_max_sync(0xffffffffu, t32);
+    if (t32 < hi32) span = ((static_cast<unsigned long long>(t32) << 32) | 0xffffffffull) - lo;
+  }
 
   while (need > 0) {
     const int s = span >= static_cast<unsigned long long>(kRegBins) ? (64 - __clzll(static_cast<long long>(span))) - 11 : 0;  // (span >> s) < 2048
     for (int i = tid; i < kRegBins; i += kRegThreads) hist[i] = 0;
+    if (tid == 0) scal[0] = 0xffffffffu;  // "no bucket reaches `need`" until the scan says otherwise
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < E; ++j) {
@@ -286,6 +312,11 @@ __global__ void __launch_bounds__(kRegThreads, E <= 32 ? 2 : 1) select_k_reg_ker
     }
     __syncthreads();
     const uint32_t bstar = scal[0], below = scal[1], inb = scal[2];
+    if (bstar == 0xffffffffu) {  // (block-uniform; first round only) the sampled bound cut below the k-th key: full span
+      span = full_span;
+      __syncthreads();
+      continue;
+    }
     const bool finish = inb <= static_cast<uint32_t>(kRegEqCap);
 #pragma unroll
     for (int j = 0; j < E; ++j) {
@@ -350,10 +381,13 @@ void launch(cudaStream_t stream, const float* in_val, const void* in_idx, int64_
     (void)carve;
     auto ii = static_cast<const IdxIn*>(in_idx);
     auto oo = static_cast<IdxOut*>(out_idx);
-    if (len <= 8 * kRegThreads) select_k_reg_kernel<8, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
-    else if (len <= 16 * kRegThreads) select_k_reg_kernel<16, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
-    else if (len <= 32 * kRegThreads) select_k_reg_kernel<32, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
-    else select_k_reg_kernel<64, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min);
+    // sample elements per thread for the kernel's sampled bound: 32 * es ~ 0.7 * len / k samples per warp (0 = no sampling)
+    static const bool no_sample = getenv("CUVS_B200_SELECT_NOSAMPLE") != nullptr;
+    const int es = no_sample ? 0 : static_cast<int>(std::min<int64_t>(64, (7 * len) / (320 * static_cast<int64_t>(std::max(k, 1)))));
+    if (len <= 8 * kRegThreads) select_k_reg_kernel<8, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min, es);
+    else if (len <= 16 * kRegThreads) select_k_reg_kernel<16, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min, es);
+    else if (len <= 32 * kRegThreads) select_k_reg_kernel<32, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min, es);
+    else select_k_reg_kernel<64, IdxIn, IdxOut, HasIdx><<<grid, kRegThreads, 0, stream>>>(in_val, ii, len, in_ld, k, out_val, oo, select_min, es);
     B2_CUDA(cudaGetLastError());
     return;
   }

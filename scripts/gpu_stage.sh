@@ -14,6 +14,13 @@ for stage in "$@"; do
     prof100m)   CUVS_B200_PROFILE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:pq_stream_scan -c 1 -f -o gpurun_out/r02_pq100m python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/prof100m.log 2>&1; echo "prof100m rc=$?" ;;
     launches100m) CUVS_B200_PROFILE=1 timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches100m.csv python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/launches100m.log 2>&1; echo "launches100m rc=$?" ;;
     profc2)     CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:pq_stream_scan -c 1 -f -o gpurun_out/r02_pqc2 python scripts/sweep_probes.py 10000000 1024 "64" > gpurun_out/profc2.log 2>&1; echo "profc2 rc=$?" ;;
+    bf)         timeout 600 python bench.py --workload brute_force --steps 10 > gpurun_out/bench_bf.log 2>&1; echo "bf rc=$?" ;;
+    c2cpu)      timeout 600 python bench.py --workload ivf_pq_c2 --steps 10 --no-aux > gpurun_out/bench_c2.log 2>&1; echo "c2cpu rc=$?" ;;
+    cagra)      timeout 900 python bench.py --workload cagra --steps 10 --no-cpu > gpurun_out/bench_cagra.log 2>&1; echo "cagra rc=$?" ;;
+    flat)       timeout 900 python bench.py --workload ivf_flat --steps 10 --no-cpu > gpurun_out/bench_flat.log 2>&1; echo "flat rc=$?" ;;
+    profcagra)  CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:cagra_search -c 1 -f -o gpurun_out/r02_cagra python bench.py --workload cagra --steps 1 --no-cpu > gpurun_out/profcagra.log 2>&1; echo "profcagra rc=$?" ;;
+    profc2tc)   CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:tc_scan_kernel -c 2 -f -o gpurun_out/r02_c2 python bench.py --workload ivf_pq_c2 --steps 1 --no-cpu --no-aux > gpurun_out/profc2tc.log 2>&1; echo "profc2tc rc=$?" ;;
+    launchesc2) CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launchesc2.csv python bench.py --workload ivf_pq_c2 --steps 1 --no-cpu --no-aux > gpurun_out/launchesc2.log 2>&1; echo "launchesc2 rc=$?" ;;
     smoke)      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     *)          echo "unknown stage $stage" ;;
   esac

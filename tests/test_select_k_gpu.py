@@ -38,7 +38,7 @@ def test_select_k_matches_oracle(batch, length, k, select_min):
 
 
 @pytest.mark.parametrize("length,k", [(2048, 48), (4096, 1), (4097, 256), (16384, 48), (20000, 100), (32768, 64), (16384, 300)])
-@pytest.mark.parametrize("kind", ["normal", "narrow", "all_equal", "three_values", "with_inf"])
+@pytest.mark.parametrize("kind", ["normal", "narrow", "all_equal", "three_values", "with_inf", "sorted_asc", "sorted_desc", "planted"])
 def test_select_k_medium_rows_register_path(length, k, kind):
     """Rows of 2k..32k elements with k <= 256 take the register-resident kernel (linear binning over the live span, crowded
     buckets re-binned): same answers as the oracle incl. the tie rule, for value distributions that stress the binning."""
@@ -53,6 +53,14 @@ def test_select_k_medium_rows_register_path(length, k, kind):
         v = np.full((batch, length), 3.25, np.float32)
     elif kind == "three_values":
         v = rng.choice(np.array([-1.0, 0.0, 7.5], np.float32), (batch, length))
+    elif kind == "planted":   # one outlier per warp inside the sample, nothing else near: fewer than k keys under the sampled bound
+        v = (100.0 + rng.standard_normal((batch, length))).astype(np.float32)
+        v[:, 0:512:32] = -1000.0 - np.arange(16, dtype=np.float32)
+        v[:, 7] = 1e6
+    elif kind in ("sorted_asc", "sorted_desc"):   # the kernel's sampled bound (first elements of every thread) misses: full-span retry
+        v = np.sort(rng.standard_normal((batch, length)).astype(np.float32), axis=1)
+        if kind == "sorted_desc":
+            v = np.ascontiguousarray(v[:, ::-1])
     else:
         v = rng.standard_normal((batch, length)).astype(np.float32)
         v[:, ::3] = np.inf
