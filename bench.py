@@ -521,15 +521,21 @@ class CagraWorkload:
                 "l2_flush": "256 MiB write between timed steps", "parallelism": "single GPU"}
 
     def roofline(self, kernel_ms, pk):
-        # upper bound of the walk's traffic: (itopk + iters*degree) vector rows + iters adjacency rows per query
+        """HBM-bound random gathers.  `achieved` = the walk's ALGORITHMIC bytes / live kernel time, where the algorithmic bytes
+        are the dram bytes ncu measured for this exact configuration (profiles/traffic.json: every byte the walk reads is a
+        first-touch row or adjacency gather — L2 hit rate 6 % — so measured dram traffic IS the algorithmic traffic); without
+        a capture for this size the SURVEY 8d upper bound (every child row fetched, no hash dedup) is used and says so."""
         iters = self.itopk + 5
         row_b = self.d * (2 if self.walk_bits == 16 else 4)  # bytes of one vector row as the walk reads it
         bytes_ub = self.nq * ((self.itopk + self.degree + iters * self.degree) * row_b + iters * self.degree * 4)
-        ach = bytes_ub / (kernel_ms * 1e-3) / 1e9
+        measured = ncu_traffic("cagra", self) if self.walk_bits == 32 else None
+        used = measured if measured else bytes_ub
+        ach = used / (kernel_ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "cagra_search_kernel (one warp per query, register bitonic top-k, smem hash)", "achieved": ach,
                 "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "peak_source": pk["src"] + " HBM copy",
-                "traffic": None, "kernel_ms": kernel_ms, "note": "achieved uses the UPPER BOUND of gathered bytes (every child row fetched); "
-                "hash-deduplicated children are not fetched, so true traffic is lower"}
+                "traffic": None, "kernel_ms": kernel_ms, "bytes_basis": "measured dram bytes per launch (ncu, profiles/traffic.json)" if measured
+                else "UPPER BOUND of gathered bytes (every child row fetched); hash-deduplicated children are not fetched, so true traffic is lower",
+                "upper_bound_bytes": bytes_ub}
 
     def cpu_baseline(self, budget_s=20.0):
         return cpu_baseline_on_slice(self.dataset, self.queries, self.k, budget_s,

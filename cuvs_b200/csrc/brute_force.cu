@@ -15,7 +15,7 @@
 //      candidate's approximate distance minus the error budget, the query is flagged;
 //   4. flagged queries (ties / duplicates at the k' boundary) are recomputed by the exact SIMT
 //      path.  Result: identical to oracle/oracle.c::oracle_knn, bit for bit.
-// Filtered search and shapes the tensor-core kernel does not cover (dim > 128, k > 24, fp16 data)
+// Filtered search and shapes the tensor-core kernel does not cover (dim > 2048, k > 64)
 // run on the exact SIMT path.
 #include "common.hpp"
 #include "exact.cuh"
@@ -221,14 +221,34 @@ __global__ void mask_filtered_kernel(int64_t* idx, float* dist, int64_t count, b
 }
 
 struct bf_cands {
-  dbuf<float> score;    // [nq, KC] raw engine scores s = hn - q.x (best first)
-  dbuf<uint32_t> pos;   // [nq, KC] row positions
+  dbuf<float> score;    // [nq, KCm] raw engine scores s = hn - q.x (best first)
+  dbuf<uint32_t> pos;   // [nq, KCm] row positions
   dbuf<float> qn;       // [nq] |q|^2
+  dbuf<float> floor;    // [nq] (KCm > KC only) min over the scan's FULL candidate lists of the list's worst kept score
+  int width = 0;        // entries per query row in score / pos (KCm, or everything the scan kept when that is less)
 };
 
-// Stage 1+2 of the search: split-bf16 tcgen05 scan over `splits` dataset ranges + merge to KC per query.
-static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q, int64_t nq, int KC, bf_cands& out)
+// floor[q] = min over the query's lists of the list's last (= worst, lists are sorted best-first) entry; a list that is not
+// full ends in +inf and constrains nothing.  Every row the scan rejected — by a list's own k'-th entry or by the bound shared
+// between the splits, which is some full list's k'-th entry at an earlier time and only ever decreases — scores above it.
+__global__ void list_floor_kernel(const float* __restrict__ cs, int64_t nq, int64_t row_stride, int KC, float* __restrict__ out)
 {
+  const int64_t q = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane  = threadIdx.x & 31;
+  if (q >= nq) return;
+  float m = INFINITY;
+  for (int64_t l = lane; l * KC < row_stride; l += 32) m = fminf(m, cs[q * row_stride + l * KC + KC - 1]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[q] = m;
+}
+
+// Stage 1+2 of the search: split-bf16 tcgen05 scan over `splits` dataset ranges (lists of KC per column half and split) +
+// merge to KCm per query (KCm == KC: the merged set's worst entry bounds everything outside it; KCm > KC, used for k above
+// the fused list length: `out.floor` carries the bound for the rows that never entered a list).
+static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q, int64_t nq, int KC, bf_cands& out, int KCm = 0)
+{
+  if (KCm <= 0) KCm = KC;
   auto stream           = res->stream;
   const int64_t nq_pad  = tc_pad_rows(nq);
   const int m_tiles     = static_cast<int>(nq_pad / 128);
@@ -265,10 +285,17 @@ static void bf_tc_candidates(resources* res, const bf_index& idx, const float* q
   tc_scan_topk(stream, res->device, qhi.data(), qlo.data(), nq_pad, idx.hi.data(), idx.lo.data(), idx.rows_pad, idx.Kp,
                idx.hx.data(), items.data(), n_items, nullptr, KC, 3, cs.data(), cp.data(), row_stride, &bnd,
                false /*equal-sized items in split-major order: static round-robin keeps each column range L2 resident*/);
-  if (row_stride > KC) {
-    out.score.alloc(static_cast<size_t>(nq) * KC, stream);
-    out.pos.alloc(static_cast<size_t>(nq) * KC, stream);
-    select_k(stream, cs.data(), cp.data(), IDX_U32, nq, row_stride, row_stride, KC, out.score.data(), out.pos.data(), IDX_U32, true);
+  if (KCm > KC) {
+    out.floor.alloc(static_cast<size_t>(nq), stream);
+    count_launch();
+    list_floor_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, stream>>>(cs.data(), nq, row_stride, KC, out.floor.data());
+    B2_CUDA(cudaGetLastError());
+  }
+  out.width = static_cast<int>(std::min<int64_t>(row_stride, KCm));
+  if (row_stride > KCm) {
+    out.score.alloc(static_cast<size_t>(nq) * KCm, stream);
+    out.pos.alloc(static_cast<size_t>(nq) * KCm, stream);
+    select_k(stream, cs.data(), cp.data(), IDX_U32, nq, row_stride, row_stride, KCm, out.score.data(), out.pos.data(), IDX_U32, true);
   } else {
     out.score = std::move(cs);
     out.pos   = std::move(cp);
@@ -321,7 +348,11 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
 
   const bool select_min = metric_is_min_close(idx.metric);
   static const bool force_exact = getenv("CUVS_B200_FORCE_EXACT") != nullptr;  // test knob
-  const bool use_tc     = idx.tc && filt.kind == 0 && k <= 24 && idx.n > 0 && !force_exact;
+  // k <= 24: fused lists of 16 / 32, merged to the list length.  24 < k <= 64 (the reference's fused range,
+  // knn_brute_force.cuh:447-451): fused lists of 32 per (column half, split), merged to 64 / 96 candidates, and the
+  // certificate additionally uses the lists' own worst entries (bf_cands::floor) — a row of the true top-k can only be missing
+  // when more than 32 of them fall into one list, which the certificate detects (flagged queries take the exact path).
+  const bool use_tc     = idx.tc && filt.kind == 0 && k <= 64 && idx.n > 0 && !force_exact;
   set_last_flagged(0);
   if (!use_tc) {
     search_exact(res, idx, q, nq, 0, k, out_idx, out_dist, filt);
@@ -332,9 +363,10 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
   }
 
   // ---- tensor-core candidate scan
-  const int KC = k <= 10 ? 16 : 32;
+  const int KC  = k <= 10 ? 16 : 32;
+  const int KCm = k <= 24 ? KC : (k <= 48 ? 64 : 96);
   bf_cands cand;
-  bf_tc_candidates(res, idx, q, nq, KC, cand);
+  bf_tc_candidates(res, idx, q, nq, KC, cand, KCm);
   const float* m_score  = cand.score.data();
   const uint32_t* m_pos = cand.pos.data();
   dbuf<float>& qn       = cand.qn;
@@ -345,7 +377,7 @@ static void bf_search(resources* res, const bf_index& idx, const DLTensor& qt, c
   B2_CUDA(cudaMemsetAsync(flags.data() + nq, 0, sizeof(int), stream));
   const bool need_xn = (idx.metric == L2Expanded || idx.metric == L2SqrtExpanded || idx.metric == CosineExpanded);
   rescore_topk(stream, q, nq, idx.d, idx.data, idx.d, idx.d, qn.data(), need_xn ? idx.norms.data() : nullptr, idx.metric,
-               m_pos, m_score, KC, nullptr, k, out_idx, out_dist, -1, am, flags.data(), flags.data() + nq);
+               m_pos, m_score, cand.width, nullptr, k, out_idx, out_dist, -1, am, flags.data(), flags.data() + nq, cand.floor.data());
 
   // ---- certified fallback for flagged queries (rare: exact ties / duplicates at the k' boundary)
   int n_flagged = 0;

@@ -28,6 +28,7 @@
 #include <library_types.h>
 
 #include "npy_io.hpp"
+#include "ptx_sm100.cuh"
 #include "exact.cuh"
 #include "select_k.cuh"
 #include "timing.hpp"
@@ -166,6 +167,12 @@ struct cagra_launch {
   uint32_t* traversed;          // [nq << traversed_bitlen], initialised to kInvalid by the host
   uint32_t traversed_bitlen;
   unsigned long long* mc_keys;  // [nq, walkers, 32] every walker's final sorted list (dist_key << 32 | id)
+  // > 0: bytes of one walk row (16-byte multiple, 16-byte aligned rows).  As soon as an iteration's fresh children are known,
+  // every lane asks the copy engine for its children's rows with ONE cp.async.bulk.prefetch.L2 each (UBLKPF): all <= 64 row
+  // gathers of the iteration are in flight at once, and the team loads below (2 rows per team in flight, register-bound at
+  // 40 registers / 3 CTAs per SM) find them in L2 instead of paying the HBM latency 8 times in a row.
+  uint32_t prefetch_row_bytes;
+  int prefetch_mode;  // 1 = per-lane prefetch.global.L2 of the row's lines, 2 = one cp.async.bulk.prefetch.L2 per row
 };
 
 // squared L2 / negative dot between the smem query and a dataset row, computed by a team of 8 lanes
@@ -389,6 +396,21 @@ __global__ void __launch_bounds__(512, (EI <= 2 ? 3 : (EI <= 4 ? 2 : 1))) cagra_
       }
     }
     __syncwarp();
+    if (p.prefetch_row_bytes != 0) {
+      for (int c = lane; c < n_new; c += 32) {
+        const uint32_t id = scand[c];
+        const void* row   = p.data16 ? static_cast<const void*>(p.data16 + static_cast<int64_t>(id) * p.ld16)
+                                     : static_cast<const void*>(p.data + static_cast<int64_t>(id) * p.ld);
+        if (p.prefetch_mode == 2) {
+          ptx::bulk_prefetch_l2(row, p.prefetch_row_bytes);  // UBLKPF: uniform-register operands -> one trip of a lane loop per row
+        } else {
+          // per-lane line prefetches (no uniform-register round trip): every 128-byte line the row touches
+          const char* r0 = static_cast<const char*>(row);
+          const char* l0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(r0) & ~uintptr_t(127));
+          for (const char* l = l0; l < r0 + p.prefetch_row_bytes; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+        }
+      }
+    }
     // ---- distances: 4 candidates per step (teams of 8 lanes), two steps in flight
     for (int c0 = 0; c0 < n_new; c0 += 8) {
       const int ca = c0 + g, cb = c0 + 4 + g;
@@ -553,6 +575,19 @@ cagra_plan make_plan(const cuvsCagraSearchParams& sp, int64_t n, int degree, int
   return pl;
 }
 
+// Row bytes for the walk's bulk L2 prefetch (0 = off): rows must start on 16-byte boundaries and be a 16-byte multiple long.
+// CUVS_B200_CAGRA_PREFETCH=0 disables it (A/B).
+static uint32_t walk_prefetch_bytes(const cagra_launch& p)
+{
+  const char* e = getenv("CUVS_B200_CAGRA_PREFETCH");  // (read per search: one process can A/B)
+  if (e != nullptr && e[0] == '0') return 0;
+  const size_t pitch = p.data16 ? static_cast<size_t>(p.ld16) * 2 : static_cast<size_t>(p.ld) * 4;
+  const uintptr_t base = p.data16 ? reinterpret_cast<uintptr_t>(p.data16) : reinterpret_cast<uintptr_t>(p.data);
+  if (pitch % 16 != 0 || base % 16 != 0) return 0;
+  const size_t row = (static_cast<size_t>(p.dim) * (p.data16 ? 2 : 4) + 15) / 16 * 16;
+  return static_cast<uint32_t>(std::min(row, pitch));
+}
+
 template <int EI, int EC, bool MULTI = false>
 void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
 {
@@ -577,6 +612,10 @@ void launch_search(cudaStream_t s, const cagra_launch& p, size_t per_warp_smem)
   B2_CUDA(cudaMemsetAsync(counter.data(), 0, sizeof(unsigned long long), s));
   cagra_launch pl = p;
   pl.work_counter = counter.data();
+  pl.prefetch_row_bytes = walk_prefetch_bytes(p);
+  // measured (10M x 96 fp32, batch 10k, one box, scripts/ab_cagra.py): off 5.73-5.75 ms, line prefetches 6.06-6.08 ms (slower: three
+  // CCTL per row and lane compete with the team loads for the LSU), bulk prefetch 5.56-5.58 ms -> the bulk form is the default
+  pl.prefetch_mode      = [] { const char* e = getenv("CUVS_B200_CAGRA_PREFETCH"); return e != nullptr && e[0] == '1' ? 1 : 2; }();
   timed_section ts("cagra_search", s);
   count_launch();
   kern<<<grid, warps * 32, smem, s>>>(pl);

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ 
                                                        const int64_t* __restrict__ src_ids, int k,
                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist,
                                                        int64_t pad_id, approx_map amap,
-                                                       int* __restrict__ flags, int* __restrict__ n_flagged)
+                                                       int* __restrict__ flags, int* __restrict__ n_flagged,
+                                                       const float* __restrict__ approx_floor)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -234,7 +235,18 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ 
     }
     if (lane == 0) {
       int flag = 0;
-      if (n_valid == kc && cand_score) {  // candidate list is full: rows outside it exist
+      bool outside = n_valid == kc;  // candidate list is full: rows outside it exist (dropped by the merge to kc)
+      if (approx_floor != nullptr && cand_score) {
+        // a second bound, in raw engine units, on the rows that never entered a candidate list (brute force with k above the
+        // fused list length: such rows are bounded by the lists' own worst entries, not by the merged set's); +inf = none
+        const float fl = approx_floor[qi];
+        if (fl < FLT_MAX) {
+          const float a = amap.sa * fl + amap.sb * qnv + amap.sc;
+          worst_approx  = !outside ? a : (select_min ? fminf(worst_approx, a) : fmaxf(worst_approx, a));
+          outside       = true;
+        }
+      }
+      if (outside && cand_score) {
         float eps = amap.eps_rel * (amap.eq * qnv + amap.ec);
         bool ok   = select_min ? (kth < worst_approx - eps) : (kth > worst_approx + eps);
         flag      = ok ? 0 : 1;
@@ -285,7 +297,7 @@ void exact_distance_tile(cudaStream_t stream, const float* q, int64_t nq, int64_
 void rescore_topk(cudaStream_t stream, const float* q, int64_t nq, int64_t ldq, const float* x, int64_t ldx, int d,
                   const float* qn, const float* xn, cuvsDistanceType metric, const uint32_t* cand_pos,
                   const float* cand_score, int kc, const int64_t* src_ids, int k, int64_t* out_idx, float* out_dist,
-                  int64_t pad_id, const approx_map& amap, int* flags, int* n_flagged)
+                  int64_t pad_id, const approx_map& amap, int* flags, int* n_flagged, const float* approx_floor)
 {
   if (nq == 0) return;
   B2_EXPECTS(kc >= 1 && kc <= kMaxCand, "rescore_topk: candidate count %d out of range", kc);
@@ -294,7 +306,7 @@ void rescore_topk(cudaStream_t stream, const float* q, int64_t nq, int64_t ldq, 
   count_launch();
   rescore_kernel<<<static_cast<unsigned>((nq + warps - 1) / warps), warps * 32, smem, stream>>>(
     q, nq, ldq, x, ldx, d, qn, xn, int(metric), cand_pos, cand_score, kc, src_ids, k, out_idx, out_dist, pad_id, amap,
-    flags, n_flagged);
+    flags, n_flagged, approx_floor);
   B2_CUDA(cudaGetLastError());
 }
 

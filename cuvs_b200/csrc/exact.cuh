@@ -52,7 +52,8 @@ struct approx_map {
 void rescore_topk(cudaStream_t stream, const float* q, int64_t nq, int64_t ldq, const float* x, int64_t ldx, int d,
                   const float* qn, const float* xn, cuvsDistanceType metric, const uint32_t* cand_pos,
                   const float* cand_score, int kc, const int64_t* src_ids, int k, int64_t* out_idx, float* out_dist,
-                  int64_t pad_id, const struct approx_map& amap, int* flags, int* n_flagged);
+                  int64_t pad_id, const struct approx_map& amap, int* flags, int* n_flagged,
+                  const float* approx_floor = nullptr /* [nq] raw engine score no row outside the candidates can beat */);
 
 /** In-place sqrt (L2Sqrt*) or sign/offset fix-ups applied after selection. */
 void postprocess_distances(cudaStream_t stream, float* dist, int64_t count, cuvsDistanceType metric);

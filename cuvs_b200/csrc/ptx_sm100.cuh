@@ -97,6 +97,13 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
     : "memory");
 }
 
+// Bulk L2 prefetch (UBLKPF): one instruction asks the copy engine to pull `bytes` (multiple of 16, 16-byte aligned source)
+// of global memory into L2.  No destination, no registers, no completion object: the later ordinary loads hit L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <uint32_t NCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result)

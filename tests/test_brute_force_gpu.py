@@ -65,7 +65,9 @@ def test_reference_label_case():
 
 @pytest.mark.parametrize("n,d,nq,k", [(20000, 128, 300, 10), (5000, 96, 130, 5), (3001, 33, 77, 1),
                                        (9000, 64, 128, 24), (1000, 128, 5, 10), (70000, 128, 257, 10),
-                                       (6000, 200, 140, 10), (4000, 768, 64, 10)])  # dims > 128: streamed k-blocks
+                                       (6000, 200, 140, 10), (4000, 768, 64, 10),  # dims > 128: streamed k-blocks
+                                       # 24 < k <= 64 (the reference's fused range): lists of 32 merged to 64 / 96 candidates
+                                       (20000, 128, 300, 40), (30000, 128, 200, 64), (3001, 64, 50, 64), (9000, 200, 64, 33)])
 @pytest.mark.parametrize("metric", ["sqeuclidean"])
 def test_exact_match_uniform(n, d, nq, k, metric):
     ds, qs = uniform(n, d, 1234), uniform(nq, d, 4321)
@@ -97,6 +99,28 @@ def test_duplicates_take_the_certified_fallback():
     dist, idx = _search(ds, qs, 10)
     rd, ri = oracle.knn(ds, qs, 10)
     assert last_flagged() == 32
+    assert (idx == ri).all() and (dist == rd).all()
+
+
+@pytest.mark.parametrize("metric", ["inner_product", "cosine", "euclidean"])
+def test_k_above_the_fused_list_length(metric):
+    """k = 48: the candidates are the merged top-64 of per-(split, column half) lists of 32; the certificate also uses the
+    lists' own worst entries, so the result is still the oracle's bit for bit."""
+    ds, _ = clustered(15000, 128, 17)
+    qs, _ = clustered(150, 128, 18)
+    dist, idx = _search(ds, qs, 48, metric)
+    rd, ri = oracle.knn(ds, qs, 48, metric)
+    assert (idx == ri).all(), f"{(idx != ri).sum()} index mismatches"
+    np.testing.assert_array_equal(dist, rd)
+    assert last_flagged() <= 8
+
+
+def test_duplicates_with_large_k_take_the_certified_fallback():
+    base = uniform(50, 128, 5)
+    ds = np.tile(base, (60, 1))  # 60 copies of every row: more than 32 exact ties inside one candidate list
+    qs = uniform(16, 128, 6)
+    dist, idx = _search(ds, qs, 40)
+    rd, ri = oracle.knn(ds, qs, 40)
     assert (idx == ri).all() and (dist == rd).all()
 
 
