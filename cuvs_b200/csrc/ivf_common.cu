@@ -26,6 +26,95 @@ __global__ void iota_items_kernel(tc_item* items, int m_tiles, int64_t n_rows, u
   items[m]      = it;
 }
 
+// (query tile, centre range) items of the fused coarse search: item i = (split i / m_tiles, query tile i % m_tiles)
+__global__ void split_items_kernel(tc_item* items, int m_tiles, int splits, int64_t nq, uint32_t tiles_total, int KCW)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_tiles * splits) return;
+  const int sp = i / m_tiles, m = i % m_tiles;
+  const uint32_t per = (tiles_total + splits - 1) / splits;
+  const uint32_t t0 = min(tiles_total, sp * per), t1 = min(tiles_total, t0 + per);
+  tc_item it;
+  it.a_row0     = m * 128;
+  it.b_row0     = t0 * 128;
+  it.n_tiles    = t1 - t0;
+  const int64_t valid = nq - static_cast<int64_t>(m) * 128;
+  it.valid_rows = valid > 128 ? 128 : static_cast<uint32_t>(valid);
+  it.out_off    = (static_cast<uint64_t>(m) * 128 * splits + sp) * KCW;
+  items[i]      = it;
+}
+
+// Fused coarse search, merge step: one CTA per query ranks the W = splits * lists * KC candidates its items kept
+// (sorted lists of KC per centre range and column half) by (score, centre id) — the order select_k imposes on the dense
+// score row, where position == centre id — and writes the n_probes best.  The scan rejects a centre only when its score is
+// not below a full list's worst entry (its own list's, or through the bound shared between a query's items, another list's at
+// an earlier time; such entries only decrease), so every centre outside the candidates scores >= floor = the minimum over
+// the full lists of their worst entry.  If the n_probes-th candidate lies STRICTLY below the floor the selection — ties
+// included — is the dense one; otherwise, or when fewer than n_probes candidates exist, the query is counted in *n_flagged
+// and the caller redoes the batch through the dense path.
+constexpr int kCoarseMergeThreads = 128;
+constexpr int kCoarseMaxW         = 1024;
+__global__ void __launch_bounds__(kCoarseMergeThreads)
+coarse_merge_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp, int W, int KC, int n_probes, uint32_t* __restrict__ probes,
+                    float* __restrict__ probe_scores, int* __restrict__ n_flagged)
+{
+  extern __shared__ unsigned long long ckeys[];
+  __shared__ float s_floor;
+  __shared__ int s_valid;
+  const int64_t q = blockIdx.x;
+  const int tid   = threadIdx.x;
+  constexpr int E = kCoarseMaxW / kCoarseMergeThreads;
+  unsigned long long mine[E];
+  int n_mine = 0;
+  if (tid == 0) s_valid = 0;
+  if (tid < 32) {
+    float m = INFINITY;
+    for (int l = tid; l * KC < W; l += 32) m = fminf(m, cs[q * W + l * KC + KC - 1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (tid == 0) s_floor = m;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int c = e * kCoarseMergeThreads + tid;
+    unsigned long long K = ~0ull;
+    if (c < W) {
+      const uint32_t pos = cp[q * W + c];
+      if (pos != 0xffffffffu) {
+        uint32_t u = __float_as_uint(cs[q * W + c]);
+        if ((u << 1) == 0) u = 0;  // -0.0 == +0.0, as in select_k
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        K = (static_cast<unsigned long long>(u) << 32) | pos;
+        ++n_mine;
+      }
+      ckeys[c] = K;
+    }
+    mine[e] = K;
+  }
+  if (n_mine) atomicAdd(&s_valid, n_mine);
+  __syncthreads();
+  int rank[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) rank[e] = 0;
+  for (int o = 0; o < W; ++o) {
+    const unsigned long long Ko = ckeys[o];  // (broadcast)
+#pragma unroll
+    for (int e = 0; e < E; ++e) rank[e] += Ko < mine[e] ? 1 : 0;
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (mine[e] != ~0ull && rank[e] < n_probes) {
+      const int c       = e * kCoarseMergeThreads + tid;
+      const float score = cs[q * W + c];
+      probes[q * n_probes + rank[e]]       = static_cast<uint32_t>(mine[e]);
+      probe_scores[q * n_probes + rank[e]] = score;
+      if (rank[e] == n_probes - 1 && !(score < s_floor)) atomicAdd(n_flagged, 1);  // (strict: also rules out boundary ties)
+    }
+  }
+  if (tid == 0 && s_valid < n_probes) atomicAdd(n_flagged, 1);
+}
+
 // best entry among the heads of the `lists` sorted candidate lists of each row
 __global__ void first_of_rows_kernel(const uint32_t* __restrict__ pos, const float* __restrict__ score, int64_t n, int KC,
                                      int lists, uint32_t* __restrict__ labels, float* __restrict__ out_scores)
@@ -425,12 +514,65 @@ void tc_rows_tmp::build(cudaStream_t s, const float* x, int64_t n_, int d_, bool
   tc_split_planes(s, x, n, d, d, Kp, hi.data(), with_lo ? lo.data() : nullptr, rows_pad, row_scale);
 }
 
+// Fused coarse search (large n_lists): instead of writing the dense [nq, n_lists] score block (655 MB at 10k x 16384) and
+// selecting from it, the scan keeps 32 candidates per (query, centre range, column half) in its epilogue — (query tile, centre
+// range) items also give the 148 SMs ~2 waves of work where one item per query tile gave 79 CTAs — and a small merge ranks
+// the 2 * splits * 32 candidates per query.  Exact (same scores, same (score, id) order as the dense select) whenever the merge
+// kernel's certificate holds for every query of the batch; returns false when the dense path has to run (one host read of
+// the flag count per search).
+static bool coarse_select_fused(resources* res, const tc_rows_tmp& q, const tc_rows& centers, int n_probes, uint32_t* probes,
+                                float* probe_scores)
+{
+  const char* env = getenv("CUVS_B200_COARSE_FUSED");  // read per call (A/B inside one process): "0" = dense path
+  if (env != nullptr && env[0] == '0') return false;
+  const int KC = 32;
+  if (n_probes > 2 * KC || centers.n < 4096) return false;
+  auto s               = res->stream;
+  const int64_t nq_pad = tc_pad_rows(q.n);
+  const int m_tiles    = static_cast<int>(nq_pad / 128);
+  const int64_t b_tiles = centers.rows_pad / 128;
+  const int sms        = res->sm_count ? res->sm_count : 148;
+  int splits = static_cast<int>(std::min<int64_t>(std::min<int64_t>(16, b_tiles / 4), (2 * sms + m_tiles - 1) / m_tiles));
+  splits     = std::max(splits, 1);
+  const int KCW = KC * tc_lists_per_item();
+  const int W   = splits * KCW;
+  if (W > kCoarseMaxW || W < n_probes) return false;
+  const int n_items = m_tiles * splits;
+  dbuf<tc_item> items(static_cast<size_t>(n_items), s);
+  count_launch();
+  split_items_kernel<<<blocks_for(n_items, 128), 128, 0, s>>>(items.data(), m_tiles, splits, q.n, static_cast<uint32_t>(b_tiles), KCW);
+  B2_CUDA(cudaGetLastError());
+  dbuf<float> cs(static_cast<size_t>(nq_pad) * W, s);
+  dbuf<uint32_t> cp(static_cast<size_t>(nq_pad) * W, s);
+  dbuf<int> bkeys(static_cast<size_t>(nq_pad) + 1, s);
+  B2_CUDA(cudaMemsetAsync(bkeys.data(), tc_bound_init_byte, sizeof(int) * nq_pad, s));
+  int* n_flagged = bkeys.data() + nq_pad;
+  B2_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), s));
+  tc_bound bnd;
+  bnd.keys = bkeys.data();
+  bnd.kth  = 0;  // lists prune at, and publish, their last (32nd) entry: that is what the merge's certificate reasons about
+  const bool three = q.lo.data() != nullptr && centers.lo.data() != nullptr;
+  tc_scan_topk(s, res->device, q.hi.data(), q.lo.data(), q.rows_pad, centers.hi.data(), centers.lo.data(), centers.rows_pad,
+               q.Kp, centers.hx.data(), items.data(), n_items, nullptr, KC, three ? 3 : 1, cs.data(), cp.data(), W, &bnd);
+  count_launch();
+  coarse_merge_kernel<<<static_cast<unsigned>(q.n), kCoarseMergeThreads, static_cast<size_t>(W) * 8, s>>>(
+    cs.data(), cp.data(), W, KC, n_probes, probes, probe_scores, n_flagged);
+  B2_CUDA(cudaGetLastError());
+  int flagged = 0;
+  B2_CUDA(cudaMemcpyAsync(&flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  return flagged == 0;
+}
+
 void coarse_select(resources* res, const tc_rows_tmp& q, const tc_rows& centers, int n_probes, uint32_t* probes,
                    float* probe_scores)
 {
   auto s = res->stream;
   if (q.n == 0) return;
   B2_EXPECTS(q.Kp == centers.Kp, "coarse_select: dimension mismatch");
+  dbuf<float> tmp_scores;
+  if (!probe_scores) { tmp_scores.alloc(static_cast<size_t>(q.n) * n_probes, s); probe_scores = tmp_scores.data(); }
+  if (coarse_select_fused(res, q, centers, n_probes, probes, probe_scores)) return;
   const int64_t nq_pad = tc_pad_rows(q.n);
   const int m_tiles    = static_cast<int>(nq_pad / 128);
   const int64_t ld     = centers.rows_pad;
@@ -442,8 +584,6 @@ void coarse_select(resources* res, const tc_rows_tmp& q, const tc_rows& centers,
   const bool three = q.lo.data() != nullptr && centers.lo.data() != nullptr;
   tc_scan_topk(s, res->device, q.hi.data(), q.lo.data(), q.rows_pad, centers.hi.data(), centers.lo.data(), centers.rows_pad,
                q.Kp, centers.hx.data(), items.data(), m_tiles, nullptr, 0, three ? 3 : 1, scores.data(), nullptr, ld);
-  dbuf<float> tmp_scores;
-  if (!probe_scores) { tmp_scores.alloc(static_cast<size_t>(q.n) * n_probes, s); probe_scores = tmp_scores.data(); }
   select_k(s, scores.data(), nullptr, IDX_NONE, q.n, centers.n, ld, n_probes, probe_scores, probes, IDX_U32, true);
 }
 

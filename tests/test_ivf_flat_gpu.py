@@ -122,3 +122,34 @@ def test_bitset_prefilter_equals_search_over_the_kept_rows():
     all_ids = np.concatenate(ids_f)
     rd, ri = oracle.ivf_flat_search(index.centers.cpu().numpy(), offsets, ds[all_ids], all_ids, qs, 8, 10, "sqeuclidean")
     assert oracle.recall_with_ties(idx, dist, ri, rd, eps=1e-3) >= 0.999
+
+
+_FUSED_CACHE = {}
+
+
+@pytest.mark.parametrize("n_probes", [20, 32, 48, 64])
+@pytest.mark.parametrize("nq", [37, 1000])
+def test_fused_coarse_search_equals_the_dense_one(n_probes, nq, monkeypatch):
+    """n_lists >= 4096 takes the fused coarse search (ivf_common.cu: per-(centre range, column half) lists of 32 kept in the scan
+    epilogue + a ranked merge, certificate for n_probes > 32) instead of the dense [nq, n_lists] score block + select_k.
+    Same scores, same (score, id) order => the probe lists, hence the search results, are identical.  Also vs the oracle."""
+    m = _mod()
+    n, d, n_lists, k = 120000, 64, 4096, 10
+    if "index" not in _FUSED_CACHE:
+        ds, centers = clustered(n, d, 21, n_centers=3000)
+        _FUSED_CACHE.update(ds=ds, centers=centers,
+                            index=m.build(m.IndexParams(n_lists=n_lists, kmeans_n_iters=4), torch.from_numpy(ds).cuda()))
+    ds, centers, index = _FUSED_CACHE["ds"], _FUSED_CACHE["centers"], _FUSED_CACHE["index"]
+    qs, _ = clustered(nq, d, 22, centers=centers)
+    q = torch.from_numpy(qs).cuda()
+    monkeypatch.setenv("CUVS_B200_COARSE_FUSED", "0")
+    d0, i0 = m.search(m.SearchParams(n_probes=n_probes), index, q, k)
+    l0 = launches()
+    monkeypatch.setenv("CUVS_B200_COARSE_FUSED", "1")
+    d1, i1 = m.search(m.SearchParams(n_probes=n_probes), index, q, k)
+    assert launches() > l0
+    d0, i0, d1, i1 = d0.cpu().numpy(), i0.cpu().numpy(), d1.cpu().numpy(), i1.cpu().numpy()
+    np.testing.assert_array_equal(i1, i0)
+    np.testing.assert_array_equal(d1, d0)
+    rd, ri = _oracle_search(index, ds, qs[:64], n_probes, k, "sqeuclidean")
+    assert oracle.recall_with_ties(i1[:64], d1[:64], ri, rd, eps=1e-3) >= 0.999
