@@ -24,6 +24,7 @@ for stage in "$@"; do
     abcagra)    timeout 600 python scripts/ab_cagra.py > gpurun_out/ab_cagra.log 2>&1; echo "abcagra rc=$?" ;;
     cagra_tests) timeout 600 python -m pytest tests/test_cagra_gpu.py -q > gpurun_out/cagra_tests.log 2>&1; echo "cagra_tests rc=$?" ;;
     profselect) CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:select_k_reg -c 1 -f -o gpurun_out/r02_selectk python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/profselect.log 2>&1; echo "profselect rc=$?" ;;
+    benchq)     timeout 900 python bench.py --no-cpu --no-aux > gpurun_out/bench_quick.log 2>&1; echo "benchq rc=$?" ;;
     smoke)      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     *)          echo "unknown stage $stage" ;;
   esac
