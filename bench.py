@@ -291,8 +291,9 @@ class IvfPqWorkload:
         self.dataset = gen_manifold(n, d, seed, rank=data_rank)
         self.queries = gen_manifold(nq, d, seed + 3087, rank=data_rank)
         t0 = time.time()
+        self.train_fraction = min(0.5, max(4_000_000, 256 * n_lists) / n)
         params = ivf_pq.IndexParams(n_lists=n_lists, pq_dim=pq_dim, pq_bits=8, kmeans_n_iters=10,
-                                    kmeans_trainset_fraction=min(0.5, max(4_000_000, 256 * n_lists) / n))
+                                    kmeans_trainset_fraction=self.train_fraction)
         if world == 1:
             self.index = ivf_pq.build(params, self.dataset)
             self.sharded = None
@@ -324,7 +325,8 @@ class IvfPqWorkload:
         from cuvs_b200.cluster import kmeans
         from cuvs_b200.distributed import Comm, ShardedIvfFlat, owner_of_list
         pq = self.pq
-        p0 = pq.IndexParams(n_lists=self.n_lists, pq_dim=self.pq_dim, pq_bits=8, kmeans_n_iters=10, add_data_on_build=False)
+        p0 = pq.IndexParams(n_lists=self.n_lists, pq_dim=self.pq_dim, pq_bits=8, kmeans_n_iters=10, add_data_on_build=False,
+                            kmeans_trainset_fraction=self.train_fraction)  # same training subsample as the 1-GPU build
         proto = pq.build(p0, self.dataset)
         quant = [proto.pq_centers.clone(), proto.centers.clone(), proto.centers_rot.clone(), proto.rotation_matrix.clone()]
         for t in quant:
