@@ -532,11 +532,14 @@ static bool coarse_select_fused(resources* res, const tc_rows_tmp& q, const tc_r
   const int m_tiles    = static_cast<int>(nq_pad / 128);
   const int64_t b_tiles = centers.rows_pad / 128;
   const int sms        = res->sm_count ? res->sm_count : 148;
-  int splits = static_cast<int>(std::min<int64_t>(std::min<int64_t>(16, b_tiles / 4), (2 * sms + m_tiles - 1) / m_tiles));
+  // enough items for ~2 waves of CTAs, and enough lists that the n_probes best are spread thin (>= 4 n_probes candidates:
+  // with only n_probes candidates the certificate could never hold and every batch would pay for both paths)
+  int splits = std::max((2 * sms + m_tiles - 1) / m_tiles, (n_probes + 15) / 16);
+  splits     = static_cast<int>(std::min<int64_t>(splits, std::min<int64_t>(16, b_tiles / 4)));
   splits     = std::max(splits, 1);
   const int KCW = KC * tc_lists_per_item();
   const int W   = splits * KCW;
-  if (W > kCoarseMaxW || W < n_probes) return false;
+  if (W > kCoarseMaxW || W < 4 * n_probes) return false;
   const int n_items = m_tiles * splits;
   dbuf<tc_item> items(static_cast<size_t>(n_items), s);
   count_launch();
