@@ -278,11 +278,13 @@ class IvfPqWorkload:
     timing_section = "pq_scan"
 
     def __init__(self, n=100_000_000, d=128, nq=10_000, k=10, n_lists=16384, pq_dim=64, n_probes=48, refine_ratio=2, seed=1234,
-                 rank=0, world=1, lut_dtype="f16", data_rank=16, resources=None):
+                 rank=0, world=1, lut_dtype="f16", data_rank=16, resources=None, shard_rows=False):
         from cuvs_b200.neighbors import brute_force, ivf_pq, refine
         self.n, self.d, self.nq, self.k = n, d, nq, k
         self.rank, self.world = rank, world
         self._res = resources
+        self.shard_rows = bool(shard_rows) and world > 1   # N > 1: keep only this rank's fp32 rows for the exact refine
+        self.local_rows = self.local_gid = None
         self.n_lists, self.pq_dim, self.n_probes, self.refine_ratio = n_lists, pq_dim, n_probes, refine_ratio
         self.data_rank = data_rank
         self.name = (f"ivf_pq {n // 1_000_000}M x {d} f32, n_lists={n_lists} pq_dim={pq_dim} pq_bits=8 n_probes={n_probes}, "
@@ -317,6 +319,9 @@ class IvfPqWorkload:
         self.gt = exact_ground_truth(self.dataset, self.queries, k)
         self.gt_check = oracle_gt_check(self.dataset, self.queries, k) if rank == 0 else None
         self.recall = None
+        if self.shard_rows:
+            self.dataset = None  # from here on the rank holds its shard only: index + its own rows + the id map
+            torch.cuda.empty_cache()
 
     def _build_shard(self, params):
         """List-sharded index: quantizers trained on rank 0 and broadcast (bit-identical on every rank), every rank keeps the
@@ -335,19 +340,38 @@ class IvfPqWorkload:
         kp = kmeans.KMeansParams(n_clusters=self.n_lists)
         ids = torch.arange(self.n, dtype=torch.int64, device="cuda")
         step = 1 << 20
+        own_rows, own_gid, n_local = [], [], 0
         for s in range(0, self.n, step):
             rows = self.dataset[s:s + step]
             labels, _ = kmeans.predict(kp, rows, quant[1])
             mine = owner_of_list(labels.to(torch.int64), self.world) == self.rank
-            pq.extend(index, rows[mine].contiguous(), ids[s:s + step][mine].contiguous())
+            r, g = rows[mine].contiguous(), ids[s:s + step][mine].contiguous()
+            if self.shard_rows:
+                # sharded memory plan: the index stores LOCAL row numbers, the rank keeps only the fp32 rows of its own lists
+                # (for the exact refine) and the local -> global id map; the full dataset is dropped after the ground truth
+                own_rows.append(r)
+                own_gid.append(g)
+                g = torch.arange(n_local, n_local + r.shape[0], dtype=torch.int64, device="cuda")
+                n_local += r.shape[0]
+            pq.extend(index, r, g)
+        if self.shard_rows:
+            self.local_rows, self.local_gid = torch.cat(own_rows), torch.cat(own_gid)
+            del own_rows, own_gid
 
         def local_search(local, sp, q, k):
             res = self._res
+            rows = self.local_rows if self.shard_rows else self.dataset
             if self.refine_ratio > 1:
                 pq.search(sp, local, q, self.kc, neighbors=self.cand, distances=self.cand_d, resources=res)
-                self.refine(self.dataset, q, self.cand, indices=self.neighbors, distances=self.distances, resources=res)
+                self.refine(rows, q, self.cand, indices=self.neighbors, distances=self.distances, resources=res)
             else:
                 pq.search(sp, local, q, k, neighbors=self.neighbors, distances=self.distances, resources=res)
+            if self.shard_rows:  # local row numbers -> global ids (pad entries, < 0 or out of range, pass through)
+                # (torch ops on the current stream = the resource's stream: bench creates Resources() on it)
+                loc = self.neighbors
+                ok = (loc >= 0) & (loc < self.local_gid.shape[0])
+                self.neighbors_g = torch.where(ok, self.local_gid[loc.clamp(0, self.local_gid.shape[0] - 1)], loc)
+                return self.distances, self.neighbors_g
             return self.distances, self.neighbors  # (no host sync: the exchange step is enqueued on the same stream)
 
         comm = Comm(self._res) if self._res is not None else None
@@ -403,7 +427,9 @@ class IvfPqWorkload:
                 "l2_flush": "256 MiB write between timed steps",
                 "parallelism": "single GPU" if self.world == 1 else
                 f"index sharded by IVF list over {self.world} GPUs (list % {self.world}), per-shard search + exact refine, one NCCL "
-                "all-gather of partial top-k + k-way merge on every rank"}
+                "all-gather of partial top-k + k-way merge on every rank; "
+                + ("every rank keeps only the fp32 rows of its own lists (local ids + id map)" if self.shard_rows
+                   else "every rank keeps the full fp32 dataset for the refine")}
 
     def dense(self):
         """The library's own rule (ivf_pq.cu: dense_probing): a small index also caches decoded rows, and a batch that sends
@@ -703,6 +729,7 @@ def run_ours(args):
             if getattr(args, name):
                 kw[name] = getattr(args, name)
         kw["rank"], kw["world"] = rank, world
+        kw["shard_rows"] = args.shard_rows
     if args.workload == "ivf_flat":
         for name in ("n_lists", "n_probes"):
             if getattr(args, name):
@@ -886,6 +913,8 @@ def main():
     ap.add_argument("--walk-bits", dest="walk_bits", type=int, default=32, choices=[16, 32],
                     help="cagra: precision of the rows the graph walk reads (16 = fp16 copy + fp32 re-rank, 32 = fp32)")
     ap.add_argument("--data-rank", dest="data_rank", type=int, default=0, help="intrinsic dimension of the synthetic manifold data (default 16)")
+    ap.add_argument("--shard-rows", dest="shard_rows", action="store_true",
+                    help="ivf_pq, N > 1: every rank keeps only the fp32 rows of the lists it owns (sharded refine) instead of the full dataset")
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary harder-data (rank-32, 10M) measurement of the ivf_pq line")
     ap.add_argument("--itopk", type=int, default=0)
     ap.add_argument("--degree", type=int, default=0)
