@@ -54,6 +54,7 @@ __global__ void split_items_kernel(tc_item* items, int m_tiles, int splits, int6
 // and the caller redoes the batch through the dense path.
 constexpr int kCoarseMergeThreads = 128;
 constexpr int kCoarseMaxW         = 1024;
+template <int E>  // candidates per thread: W <= E * kCoarseMergeThreads
 __global__ void __launch_bounds__(kCoarseMergeThreads)
 coarse_merge_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ cp, int W, int KC, int n_probes, uint32_t* __restrict__ probes,
                     float* __restrict__ probe_scores, int* __restrict__ n_flagged)
@@ -63,7 +64,6 @@ coarse_merge_kernel(const float* __restrict__ cs, const uint32_t* __restrict__ c
   __shared__ int s_valid;
   const int64_t q = blockIdx.x;
   const int tid   = threadIdx.x;
-  constexpr int E = kCoarseMaxW / kCoarseMergeThreads;
   unsigned long long mine[E];
   int n_mine = 0;
   if (tid == 0) s_valid = 0;
@@ -558,8 +558,17 @@ static bool coarse_select_fused(resources* res, const tc_rows_tmp& q, const tc_r
   tc_scan_topk(s, res->device, q.hi.data(), q.lo.data(), q.rows_pad, centers.hi.data(), centers.lo.data(), centers.rows_pad,
                q.Kp, centers.hx.data(), items.data(), n_items, nullptr, KC, three ? 3 : 1, cs.data(), cp.data(), W, &bnd);
   count_launch();
-  coarse_merge_kernel<<<static_cast<unsigned>(q.n), kCoarseMergeThreads, static_cast<size_t>(W) * 8, s>>>(
-    cs.data(), cp.data(), W, KC, n_probes, probes, probe_scores, n_flagged);
+  {
+    const unsigned grid = static_cast<unsigned>(q.n);
+    const size_t smem   = static_cast<size_t>(W) * 8;
+    const int per       = (W + kCoarseMergeThreads - 1) / kCoarseMergeThreads;
+#define B2_CM(E_) coarse_merge_kernel<E_><<<grid, kCoarseMergeThreads, smem, s>>>(cs.data(), cp.data(), W, KC, n_probes, probes, probe_scores, n_flagged)
+    if (per <= 1) B2_CM(1);
+    else if (per <= 2) B2_CM(2);
+    else if (per <= 4) B2_CM(4);
+    else B2_CM(8);
+#undef B2_CM
+  }
   B2_CUDA(cudaGetLastError());
   int flagged = 0;
   B2_CUDA(cudaMemcpyAsync(&flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
