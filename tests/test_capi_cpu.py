@@ -159,3 +159,29 @@ def test_cpp_header_adaptor_search_on_the_gpu(tmp_path):
     _build_cpp_client(exe)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "CPP_ADAPTOR_OK" in out.stdout, out.stdout + out.stderr
+
+
+def _build_bench_algo_demo(out):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", os.path.join(root, "examples", "cpp", "bench_algo_demo.cpp"),
+           "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include", "-L" + os.path.join(root, "cuvs_b200", "lib"), "-lcuvs_c",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(root, "cuvs_b200", "lib"), "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_bench_algo_wrappers_compile_and_link(tmp_path):
+    """include/cuvs_b200/bench_algo.hpp: the reference harness's `algo<T>` interface (cpp/bench/ann/src/common/ann_types.hpp:83-166)
+    and its cuvs_ivf_pq / cuvs_ivf_flat / brute-force wrappers (cpp/bench/ann/src/cuvs/*_wrapper.h) over the C ABI."""
+    exe = tmp_path / "bench_algo_demo"
+    _build_bench_algo_demo(exe)
+    out = subprocess.run([str(exe), "--no-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and "algo<T> wrappers" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_bench_algo_wrappers_run_the_harness_sequence_on_the_gpu(tmp_path):
+    exe = tmp_path / "bench_algo_demo"
+    _build_bench_algo_demo(exe)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "BENCH_ALGO_OK" in out.stdout, out.stdout + out.stderr
