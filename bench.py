@@ -901,7 +901,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ivf_pq", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=0,
+                    help="dataset rows (under torchrun use --rows: torchrun's own parser rejects --n as an ambiguous abbreviation)")
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--n-lists", dest="n_lists", type=int, default=0)
