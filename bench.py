@@ -914,8 +914,11 @@ def main():
     ap.add_argument("--walk-bits", dest="walk_bits", type=int, default=32, choices=[16, 32],
                     help="cagra: precision of the rows the graph walk reads (16 = fp16 copy + fp32 re-rank, 32 = fp32)")
     ap.add_argument("--data-rank", dest="data_rank", type=int, default=0, help="intrinsic dimension of the synthetic manifold data (default 16)")
-    ap.add_argument("--shard-rows", dest="shard_rows", action="store_true",
-                    help="ivf_pq, N > 1: every rank keeps only the fp32 rows of the lists it owns (sharded refine) instead of the full dataset")
+    ap.add_argument("--no-shard-rows", dest="shard_rows", action="store_false",
+                    help="ivf_pq, N > 1: keep the full fp32 dataset on every rank for the refine (default: every rank keeps only the rows "
+                         "of the lists it owns — local ids + an id map — and drops the dataset after the ground truth is computed)")
+    ap.add_argument("--shard-rows", dest="shard_rows", action="store_true", help="(default) see --no-shard-rows")
+    ap.set_defaults(shard_rows=True)
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary harder-data (rank-32, 10M) measurement of the ivf_pq line")
     ap.add_argument("--itopk", type=int, default=0)
     ap.add_argument("--degree", type=int, default=0)

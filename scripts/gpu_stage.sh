@@ -26,7 +26,7 @@ for stage in "$@"; do
     profselect) CUVS_B200_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:select_k_reg -c 1 -f -o gpurun_out/r02_selectk python scripts/sweep_probes.py 100000000 16384 "48" > gpurun_out/profselect.log 2>&1; echo "profselect rc=$?" ;;
     benchq)     timeout 900 python bench.py --no-cpu --no-aux > gpurun_out/bench_quick.log 2>&1; echo "benchq rc=$?" ;;
     mgtests)    timeout 600 python -m pytest tests/test_mg_gpu.py tests/test_distributed_nccl.py -q > gpurun_out/mg_tests.log 2>&1; echo "mgtests rc=$?" ;;
-    bench2)     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --rows 20000000 --n-lists 4096 --no-aux --shard-rows > gpurun_out/bench_n2.log 2>&1; echo "bench2 rc=$?" ;;
+    bench2)     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --rows 20000000 --n-lists 4096 --no-aux > gpurun_out/bench_n2.log 2>&1; echo "bench2 rc=$?" ;;
     fusedtest)  timeout 600 python -m pytest tests/test_ivf_flat_gpu.py -q -k "fused or matches_oracle" > gpurun_out/fused_tests.log 2>&1; echo "fusedtest rc=$?" ;;
     smoke)      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     *)          echo "unknown stage $stage" ;;
