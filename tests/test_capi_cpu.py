@@ -177,11 +177,3 @@ def test_bench_algo_wrappers_compile_and_link(tmp_path):
     _build_bench_algo_demo(exe)
     out = subprocess.run([str(exe), "--no-gpu"], capture_output=True, text=True)
     assert out.returncode == 0 and "algo<T> wrappers" in out.stdout, out.stdout + out.stderr
-
-
-@pytest.mark.gpu
-def test_bench_algo_wrappers_run_the_harness_sequence_on_the_gpu(tmp_path):
-    exe = tmp_path / "bench_algo_demo"
-    _build_bench_algo_demo(exe)
-    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "BENCH_ALGO_OK" in out.stdout, out.stdout + out.stderr
