@@ -201,7 +201,9 @@ def cpu_exact_knn_rate(ds_rows, qs, k, budget_s, what, n_total=None):
         r = subprocess.run([sys.executable, script, f_ds, f_q, str(k), "1"], env=env, capture_output=True, text=True, timeout=600)
         probe = json.loads(r.stdout.strip().splitlines()[-1])
         rate = max(probe["probe_rates_qps"].values())
-        m = int(max(16, min(len(qs), budget_s / 4.0 * rate)))
+        # at least one full 256-query block: the workload is a 10k-query BATCH, and a skinny GEMM (a few dozen queries per pass
+        # over the rows) would measure the host's memory bandwidth, not what a tuned CPU brute force does with the batch
+        m = int(min(len(qs), max(256, budget_s / 4.0 * rate)))
         np.save(f_q, np.ascontiguousarray(qs[:m]))
         r = subprocess.run([sys.executable, script, f_ds, f_q, str(k), "3", probe["formulation"]], env=env, capture_output=True,
                            text=True, timeout=900)
