@@ -42,6 +42,25 @@ def _dataset(n=10_000, d=128, nq=500, k=10, seed=7):
                       distance_metric="euclidean")
 
 
+def _c0_dataset_with_the_reference_ground_truth():
+    """10k x 128 f32, k = 10, with the ground truth the REFERENCE's CPU path computed (cuvs_bench generate_groundtruth
+    calc_truth, run by oracle/make_golden_cuvs_bench.py; tests/golden/cuvs_bench_cpu_groundtruth.json, case c0_10k_x_128_l2)."""
+    case = [c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                   "cuvs_bench_cpu_groundtruth.json")))["cases"] if c["name"] == "c0_10k_x_128_l2"][0]
+    rng = np.random.default_rng(case["seed"])
+    base = rng.standard_normal((case["n"], case["d"]), dtype=np.float32)
+    queries = rng.standard_normal((case["nq"], case["d"]), dtype=np.float32)
+    return bb.Dataset(name="c0-10k-128-euclidean", training_vectors=base, query_vectors=queries,
+                      groundtruth_neighbors=np.array(case["ids"]), distance_metric="euclidean")
+
+
+def test_c0_harness_recall_against_the_reference_cpu_ground_truth():
+    ds = _c0_dataset_with_the_reference_ground_truth()
+    recs = bb.run_config({"name": "cpu_exact", "groups": {"base": {"build": {}, "search": {}}}}, ds, k=10, batch_size=50,
+                         mode="throughput", backend=OracleExactBackend({"name": "cpu_exact"}))
+    assert recs[1]["Recall"] >= 0.999 and recs[1]["n_queries"] == 100
+
+
 def test_c0_plumbing_10k_x_128_k10_on_cpu():
     ds = _dataset()
     cfg = {"name": "cpu_exact", "groups": {"base": {"build": {}, "search": {}}}}

@@ -124,6 +124,25 @@ def test_duplicates_with_large_k_take_the_certified_fallback():
     assert (idx == ri).all() and (dist == rd).all()
 
 
+def _ref_exec_cases():
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cuvs_bench_cpu_groundtruth.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", _ref_exec_cases(), ids=lambda c: c["name"])
+def test_matches_the_reference_cpu_search_outputs(case):
+    """Fixtures = outputs of the reference's own CPU exact search (cuvs_bench generate_groundtruth cpu_search / calc_truth, run in
+    the build container by oracle/make_golden_cuvs_bench.py) on seeded inputs regenerated here; the first case has BASELINE
+    configs[0]'s shape (10k x 128, k = 10)."""
+    rng = np.random.default_rng(case["seed"])
+    ds = rng.standard_normal((case["n"], case["d"]), dtype=np.float32)
+    qs = rng.standard_normal((case["nq"], case["d"]), dtype=np.float32)
+    metric = "sqeuclidean" if case["metric"] == "squeclidean" else "inner_product"
+    dist, idx = _search(ds, qs, case["k"], metric)
+    ri, rd = np.array(case["ids"]), np.array(case["distances"], np.float32)
+    np.testing.assert_allclose(dist, rd, rtol=2e-5, atol=1e-5)
+    assert (idx == ri).mean() >= 0.999
+
+
 def test_fewer_rows_than_k():
     ds = np.eye(3, 16, dtype=np.float32)
     dist, idx = _search(ds, ds[:2], 5)

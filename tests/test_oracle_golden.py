@@ -127,3 +127,34 @@ def test_blocked_gemm_formulation_agrees_with_the_pinned_scan():
         assert oracle.recall_with_ties(i1, d1, i0, d0, eps=1e-3) >= 0.9999
         assert (i0 == i1).mean() >= 0.999
         np.testing.assert_allclose(d1, d0, rtol=1e-4, atol=2e-4)
+
+
+# ---- fixtures produced by the REFERENCE's own CPU search, executed in the build container (oracle/make_golden_cuvs_bench.py)
+def _ref_exec_cases():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cuvs_bench_cpu_groundtruth.json")
+    return json.load(open(path))["cases"]
+
+
+def _ref_exec_inputs(case):
+    rng = np.random.default_rng(case["seed"])  # the same Generator calls as oracle/make_golden_cuvs_bench.py: inputs()
+    ds = rng.standard_normal((case["n"], case["d"]), dtype=np.float32)
+    qs = rng.standard_normal((case["nq"], case["d"]), dtype=np.float32)
+    return ds, qs
+
+
+@pytest.mark.parametrize("case", _ref_exec_cases(), ids=lambda c: c["name"])
+def test_oracle_knn_reproduces_the_reference_cpu_search(case):
+    """python/cuvs_bench/cuvs_bench/generate_groundtruth/__main__.py:104-214 (cpu_search / calc_truth, numpy) is the one CPU
+    implementation of exact kNN the reference ships.  Its outputs on seeded inputs are committed; the oracle must return the
+    same neighbours (the reference sums in numpy's pairwise order, the oracle in fmaf chains: distances to 1e-5 relative,
+    ids identical except where two distances tie within that tolerance)."""
+    ds, qs = _ref_exec_inputs(case)
+    metric = "sqeuclidean" if case["metric"] == "squeclidean" else "inner_product"
+    d, i = oracle.knn(ds, qs, case["k"], metric)
+    ri, rd = np.array(case["ids"]), np.array(case["distances"], np.float32)
+    np.testing.assert_allclose(d, rd, rtol=2e-5, atol=1e-5)
+    same = (i == ri)
+    assert same.mean() >= 0.999, f"{(~same).sum()} of {same.size} neighbour ids differ from the reference's CPU search"
+    for q, j in zip(*np.nonzero(~same)):  # a differing slot must be a tie within the arithmetic tolerance
+        assert abs(float(d[q, j]) - float(rd[q, j])) <= 2e-5 * max(1.0, abs(float(rd[q, j])))
+        assert set(i[q].tolist()) == set(ri[q].tolist()) or abs(float(rd[q, -1]) - float(d[q, -1])) <= 2e-5 * max(1.0, abs(float(rd[q, -1])))
