@@ -320,8 +320,60 @@ class CuvsB200Backend(HarnessMixin, BenchmarkBackend):
         return d.cpu().numpy(), i.cpu().numpy().astype(np.int64)
 
 
+def make_config_loader(algo_prefix: str = "cuvs_", backend_type: str = "cuvs_b200"):
+    """A ConfigLoader for the reference's orchestrator (orchestrator/config_loaders.py:128-260): the shared base class loads the
+    dataset YAML and expands the parameter grids; the two hooks below pick the algorithm YAML files this backend serves (names
+    starting with `algo_prefix`, from the bundled config/algos directory plus `algorithm_configuration`) and turn every build
+    combination into one IndexConfig / BenchmarkConfig — the same shape the OpenSearch loader produces
+    (backends/opensearch.py:31-205).  Only available when the reference's cuvs_bench package is importable."""
+    from cuvs_bench.orchestrator.config_loaders import BenchmarkConfig, ConfigLoader  # type: ignore
+    from cuvs_bench.orchestrator.config_loaders import IndexConfig as RefIndexConfig  # type: ignore
+    import cuvs_bench.backends as _ref_backends  # type: ignore
+
+    class Loader(ConfigLoader):
+        def __init__(self, config_path=None):
+            self.config_path = os.fspath(config_path) if config_path is not None else os.path.join(os.path.dirname(os.path.realpath(_ref_backends.__file__)), "..", "config")  # the bundled config dir, as backends/opensearch.py:52-58 locates it
+
+        @property
+        def backend_type(self) -> str:
+            return backend_type
+
+        def _discover_algo_groups(self, dataset_conf, dataset, dataset_path, **kwargs):
+            files = [f for f in self.gather_algorithm_configs(self.config_path, kwargs.get("algorithm_configuration"))
+                     if os.path.basename(f).startswith(algo_prefix)]
+            allowed_algos = [a.strip() for a in kwargs["algorithms"].split(",")] if kwargs.get("algorithms") else None
+            allowed_groups = [g.strip() for g in kwargs["groups"].split(",")] if kwargs.get("groups") else None
+            out = []
+            for f in files:
+                conf = self.load_yaml_file(f)
+                name = conf.get("name", "")
+                if allowed_algos and name not in allowed_algos:
+                    continue
+                for gname, gconf in conf.get("groups", {}).items():
+                    if allowed_groups and gname not in allowed_groups:
+                        continue
+                    out.append((name, gname, gconf, {}))
+            return out
+
+        def _build_benchmark_configs(self, dataset_config, dataset_conf, dataset, dataset_path, expanded_groups, **kwargs):
+            configs = []
+            for algo_name, group_name, _conf, build_combos, search_combos, _meta in expanded_groups:
+                for bp in build_combos or [{}]:
+                    prefix = algo_name if group_name == "base" else f"{algo_name}_{group_name}"
+                    label = ".".join([prefix] + [f"{k}{v}" for k, v in bp.items()])
+                    ix = RefIndexConfig(name=label, algo=algo_name, build_param=bp, search_params=search_combos or [{}],
+                                        file=os.path.join(dataset_path, dataset, "index", label))
+                    configs.append(BenchmarkConfig(indexes=[ix], backend_config={"name": label, "algo": algo_name,
+                                                                                 "requires_gpu": algo_prefix == "cuvs_"}))
+            return configs
+
+    return Loader
+
+
 def register(name: str = "cuvs_b200") -> bool:
-    """Register the backend with the reference's plugin registry (backends/registry.py); False when cuvs_bench is absent."""
+    """Register the backend AND its config loader with the reference's registries (backends/registry.py: register_backend,
+    register_config_loader), after which `BenchmarkOrchestrator(backend_type=name).run_benchmark(...)` drives this library.
+    False when cuvs_bench is absent."""
     if not HAVE_CUVS_BENCH:
         return False
     from cuvs_bench.backends.registry import get_registry  # type: ignore
@@ -330,6 +382,11 @@ def register(name: str = "cuvs_b200") -> bool:
         reg.register(name, CuvsB200Backend)
     except ValueError:
         pass  # already registered
+    try:
+        from cuvs_bench.backends.registry import register_config_loader  # type: ignore
+        register_config_loader(name, make_config_loader("cuvs_", name))
+    except Exception:  # noqa: BLE001 - older registry without config loaders, or already registered
+        pass
     return True
 
 

@@ -139,3 +139,80 @@ def test_plugin_is_a_backend_of_the_reference_package():
     finally:
         if REF_PKG in sys.path:
             sys.path.remove(REF_PKG)
+
+
+def test_c0_through_the_reference_orchestrator(tmp_path):
+    """BASELINE configs[0] end to end through the REFERENCE's own benchmark code: cuvs_bench's BenchmarkOrchestrator
+    (orchestrator/orchestrator.py:27-290) loads a dataset YAML + an algorithm YAML, expands the parameter grid with its own
+    ConfigLoader base class, reads the .fbin / .ibin files with its own loader and drives a backend registered through its
+    registry — here the plugin's harness with the test-only CPU searcher, on 10k x 128 f32, k = 10, with the ground truth the
+    reference's CPU path computed.  Skipped where the reference checkout is absent."""
+    if not os.path.isdir(REF_PKG):
+        pytest.skip("no reference checkout on this box")
+    yaml = pytest.importorskip("yaml")
+    case = [c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                   "cuvs_bench_cpu_groundtruth.json")))["cases"] if c["name"] == "c0_10k_x_128_l2"][0]
+    rng = np.random.default_rng(case["seed"])
+    base = rng.standard_normal((case["n"], case["d"]), dtype=np.float32)
+    queries = rng.standard_normal((case["nq"], case["d"]), dtype=np.float32)
+
+    def write_bin(path, a):  # cuvs-bench binary format, legacy header (cuvs_bench/_bin_format.py): uint32 rows, uint32 cols, data
+        with open(path, "wb") as f:
+            np.array(a.shape, dtype=np.uint32).tofile(f)
+            np.ascontiguousarray(a).tofile(f)
+
+    ddir = tmp_path / "c0"
+    ddir.mkdir()
+    write_bin(ddir / "base.fbin", base)
+    write_bin(ddir / "query.fbin", queries)
+    write_bin(ddir / "groundtruth.neighbors.ibin", np.array(case["ids"], dtype=np.int32))
+    ds_yaml = tmp_path / "datasets.yaml"
+    ds_yaml.write_text(yaml.safe_dump([{"name": "c0", "base_file": "c0/base.fbin", "query_file": "c0/query.fbin",
+                                        "groundtruth_neighbors_file": "c0/groundtruth.neighbors.ibin", "dims": case["d"],
+                                        "distance": "euclidean"}]))
+    adir = tmp_path / "algos"
+    adir.mkdir()
+    (adir / "cpu_exact.yaml").write_text(yaml.safe_dump({"name": "cpu_exact", "groups": {"base": {"build": {"dummy": [1]}, "search": {"ef": [10, 20]}}}}))
+
+    sys.path.insert(0, REF_PKG)
+    try:
+        try:
+            importlib.import_module("cuvs_bench.orchestrator")
+        except Exception as e:  # noqa: BLE001
+            pytest.skip(f"reference cuvs_bench.orchestrator not importable here: {e}")
+        mod = importlib.reload(bb)
+        try:
+            if not mod.HAVE_CUVS_BENCH:
+                pytest.skip("reference cuvs_bench.backends not importable here")
+            from cuvs_bench.backends.registry import get_registry, register_config_loader
+            from cuvs_bench.orchestrator import BenchmarkOrchestrator
+
+            class CpuExact(mod.HarnessMixin, mod.BenchmarkBackend):
+                def _build_one(self, algo, metric, vectors, build_param):
+                    return (np.ascontiguousarray(vectors, dtype=np.float32), metric)
+
+                def _search_batch(self, handle, algo, q, k, search_param, dataset):
+                    return oracle.knn(handle[0], np.ascontiguousarray(q, dtype=np.float32), k, handle[1])
+
+            try:
+                get_registry().register("cpu_exact_test", CpuExact)
+            except ValueError:
+                pass
+            register_config_loader("cpu_exact_test", mod.make_config_loader("cpu_exact", "cpu_exact_test"))
+            results = BenchmarkOrchestrator(backend_type="cpu_exact_test").run_benchmark(
+                mode="sweep", dataset="c0", dataset_path=str(tmp_path), dataset_configuration=str(ds_yaml),
+                algorithm_configuration=str(adir), algorithms="cpu_exact", count=10, batch_size=50, search_mode="throughput")
+            assert len(results) == 2 and results[0].success and results[1].success
+            build, search = results
+            assert build.to_json()["name"] == "cpu_exact/build"
+            assert search.recall >= 0.999 and search.neighbors.shape == (case["nq"], 10)
+            assert len(search.metadata["all_results"]) == 2  # two search-parameter combinations of the YAML grid
+            assert search.to_json()["items_per_second"] > 0
+        finally:
+            for name in [m for m in sys.modules if m == "cuvs_bench" or m.startswith("cuvs_bench.")]:
+                del sys.modules[name]
+            sys.path.remove(REF_PKG)
+            importlib.reload(bb)
+    finally:
+        if REF_PKG in sys.path:
+            sys.path.remove(REF_PKG)
