@@ -216,3 +216,30 @@ def test_c0_through_the_reference_orchestrator(tmp_path):
     finally:
         if REF_PKG in sys.path:
             sys.path.remove(REF_PKG)
+
+
+def test_recall_and_grid_expansion_agree_with_the_reference_helpers():
+    """bb.recall_at_k vs cuvs_bench.backends._utils.compute_recall, and run_config's Cartesian expansion vs expand_param_grid
+    (python/cuvs_bench/cuvs_bench/backends/_utils.py:125-215), on random inputs — executed against the reference package."""
+    if not os.path.isdir(REF_PKG):
+        pytest.skip("no reference checkout on this box")
+    sys.path.insert(0, REF_PKG)
+    try:
+        try:
+            ref = importlib.import_module("cuvs_bench.backends._utils")
+        except Exception as e:  # noqa: BLE001
+            pytest.skip(f"reference helpers not importable here: {e}")
+        rng = np.random.default_rng(3)
+        for k, gtk in [(8, 16), (10, 10), (1, 5), (12, 12)]:  # set recall over the first k ground-truth ids (_utils.py:156-204)
+            found = np.stack([rng.permutation(40)[:k] for _ in range(25)])
+            truth = np.stack([rng.permutation(40)[:gtk] for _ in range(25)])
+            assert bb.recall_at_k(found, truth, k) == pytest.approx(ref.compute_recall(found, truth, k))
+        grid = {"nlist": [1024, 2048], "pq_dim": [64, 32], "ratio": [10]}
+        mine = [dict(zip(sorted(grid), vals)) for vals in __import__("itertools").product(*[grid[x] for x in sorted(grid)])]
+        theirs = ref.expand_param_grid(grid)
+        assert sorted(map(lambda d: sorted(d.items()), mine)) == sorted(map(lambda d: sorted(d.items()), theirs))
+    finally:
+        for name in [m for m in sys.modules if m == "cuvs_bench" or m.startswith("cuvs_bench.")]:
+            del sys.modules[name]
+        if REF_PKG in sys.path:
+            sys.path.remove(REF_PKG)
