@@ -78,7 +78,10 @@ __host__ __device__ __forceinline__ uint64_t xorshift64(uint64_t u)
   return u * 0x2545F4914F6CDD1DULL;
 }
 
-// hashmap.hpp:37-73 — open addressing, double hashing; returns 1 when newly inserted
+// hashmap.hpp:37-73 — open addressing; returns 1 when newly inserted.  The reference file carries two probing schemes and
+// compiles the linear one (#define HASHMAP_LINEAR_PROBING: index = (key ^ (key >> bitlen)) & mask, stride 1); this is its
+// double-hashing branch (hashmap.hpp:52-55).  Both are exact sets while the table is not full (the plan keeps the fill rate
+// <= 50 %, search_plan.cuh:256-372), so visited-set semantics — and therefore the walk — do not depend on the choice.
 __device__ __forceinline__ uint32_t hash_insert(uint32_t* table, uint32_t bitlen, uint32_t key)
 {
   const uint32_t size = 1u << bitlen, mask = size - 1;

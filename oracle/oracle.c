@@ -387,7 +387,9 @@ static inline uint64_t xorshift64(uint64_t u)
   u ^= u >> 12; u ^= u << 25; u ^= u >> 27;
   return u * 0x2545F4914F6CDD1DULL;
 }
-/* hashmap.hpp:37-73 (double hashing, open addressing) */
+/* hashmap.hpp:37-73, open addressing.  The reference compiles its linear-probing variant (HASHMAP_LINEAR_PROBING); this is
+ * the double-hashing branch of the same file (:52-55).  Both are exact sets below capacity, which the search plan guarantees
+ * (fill rate <= 50 %), so the walk does not depend on the probing scheme. */
 static int hash_insert(uint32_t* table, uint32_t bitlen, uint32_t key)
 {
   const uint32_t size = 1u << bitlen, mask = size - 1;
